@@ -1,0 +1,180 @@
+/*
+ * ilcc2_b200.h -- C ABI of the B200-native LiDAR chessboard-corner extractor (libilcc2_b200.so).
+ *
+ * Drop-in boundary for ONE path of icameling/lidar_camera_calibration: what the ilcc2 node
+ * ilcc2/test/get_lidar_corners.cpp:183-198 does with a LidarCornersEst object between receiving a
+ * PointCloud2 + clicked point and writing process_data/<cam>_lidar_<i>.txt:
+ *
+ *     setROI(cloud, click)      ilcc2/src/LidarCornersEst.cpp:48-70
+ *     EuclideanCluster()        ilcc2/src/LidarCornersEst.cpp:124-186   (+ getPlane :190-221)
+ *     PCA()                     ilcc2/src/LidarCornersEst.cpp:366-372   (+ transformbyPCA :330-364, get_gray_zone/calHist :224-328)
+ *     get_corners(corners)      ilcc2/src/LidarCornersEst.cpp:374-450   (+ Optimization::get_theta_t, Optimization.cpp:94-160,
+ *                                                                         VirtualboardError, Optimization.h:12-121, getPCDcorners :501-556)
+ *     save_corners2txt(...)     ilcc2/test/get_lidar_corners.cpp:27-36
+ *
+ * The reference has no FFI; its seam is that C++ class (ilcc2/include/ilcc2/LidarCornersEst.h:40-67).
+ * This header is what a binding for that seam calls; include/ilcc2_b200/LidarCornersEst.hpp is the
+ * source-compatible C++ adaptor and INTEGRATION.md shows the reference-side change.
+ *
+ * All entry points are plain C: pointers, sizes, no C++/torch types.  The GUI key presses of the
+ * reference (Visualization.cpp:20-57) become per-frame flags.  There is no CPU fallback: every compute
+ * entry point fails with ILCC2_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef ILCC2_B200_H_
+#define ILCC2_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ILCC2_VERSION 100
+
+/* ---- function return codes (0 = success) ---- */
+enum {
+  ILCC2_SUCCESS = 0,
+  ILCC2_ERR_INVALID_ARGUMENT = 1,
+  ILCC2_ERR_CUDA = 2,          /* CUDA runtime error or no usable device; see ilcc2_last_error */
+  ILCC2_ERR_CAPACITY = 3,      /* more frames / points than the handle was created for */
+  ILCC2_ERR_IO = 4
+};
+
+/* ---- per-frame status (status_out); the reference's bool returns / exceptions / UB cases ---- */
+enum {
+  ILCC2_OK = 0,
+  ILCC2_NO_POINTS_IN_ROI = 1,     /* setROI left nothing */
+  ILCC2_NO_CLUSTER = 2,           /* cluster_indices empty: reference throws std::out_of_range (:167) */
+  ILCC2_PLANE_TOO_SMALL = 3,      /* fewer plane inliers than min_board_points (online gate, :111) or < 3 */
+  ILCC2_DEGENERATE_INTENSITY = 4, /* max==min (division by zero, :235) or the mode walk runs off the map (:266-282) */
+  ILCC2_NO_OPT_POINTS = 5,        /* every board point fell in the gray zone */
+  ILCC2_RANSAC_FAILED = 6         /* no non-degenerate 3-point sample */
+};
+
+/* ---- per-frame flags = the reference's key presses ---- */
+#define ILCC2_FLAG_TOPLEFT_WHITE 1u /* 'd' once: re-optimise with topleftWhite=true, warm-started (:398-409) */
+#define ILCC2_FLAG_INVERSE       2u /* 'a' once: swap (W,H) in the corner lattice only (:394-397, :504-507) */
+#define ILCC2_FLAG_AUTO          4u /* unattended: both colour hypotheses from zero, keep the lower final cost */
+
+/* ---- where the caller's buffers live ---- */
+#define ILCC2_MEM_HOST   0 /* points/clicks/flags/outputs are host pointers; the call returns when outputs are valid */
+#define ILCC2_MEM_DEVICE 1 /* all of them are device pointers on the handle's device; asynchronous on `stream` */
+
+/* Algorithm constants. ilcc2_default_params() fills the literals hard-coded in the reference. */
+typedef struct ilcc2_params {
+  float roi_half_x;              /* 1.0   LidarCornersEst.cpp:59 */
+  float roi_half_y;              /* 1.5   :64 */
+  float roi_half_z;              /* 2.0   :54 */
+  float cluster_tolerance;       /* 0.12  :131   (0.10 in get_chessboard_by_point, :79) */
+  int32_t min_cluster_size;      /* 100   :132 */
+  int32_t max_cluster_size;      /* 25000 :133 */
+  double ransac_threshold;       /* 0.03  :201 */
+  int32_t ransac_max_iterations; /* 50    pcl::SACSegmentation default */
+  double ransac_probability;     /* 0.99  pcl::SACSegmentation default */
+  int32_t hist_bins;             /* 100   :226 */
+  double gray_rate;              /* 2.5   :371 */
+  double huber_delta;            /* 0.1   Optimization.cpp:137 */
+  double grid_length;            /* 0.15  config/pointgrey.yaml:17 */
+  int32_t cells_x;               /* (corner_in_x+1, corner_in_y+1) sorted ascending -> (6, 8)  :31-39 */
+  int32_t cells_y;
+  int32_t min_board_points;      /* 0 offline; 500 reproduces the online gate (:111) */
+  int32_t max_solver_iterations; /* 50    ceres::Solver::Options default */
+} ilcc2_params;
+
+/* Optional per-frame diagnostics (what the reference prints to stdout, plus solver state). */
+typedef struct ilcc2_diag {
+  int32_t status;
+  int32_t n_roi;             /* points kept by setROI */
+  int32_t nn_index;          /* ROI index of the click's nearest neighbour (:141) */
+  int32_t n_clusters;        /* clusters with min<=size<=max */
+  int32_t click_in_cluster;  /* 1 if that neighbour lies in a kept cluster (:144-153) */
+  int32_t cluster_rank;      /* size-descending rank of the chosen cluster (= m_plane_index) */
+  int32_t n_cluster_pts;
+  int32_t ransac_iterations;
+  int32_t n_ransac_inliers;  /* inliers of the best 3-point model */
+  int32_t n_board;           /* "chessboard plane size" (:184) */
+  int32_t n_opt;             /* black + white points (gray ones are skipped, Optimization.cpp:122-125) */
+  int32_t hyp_chosen;        /* 0: topleftWhite=false, 1: true */
+  int32_t iters[2][2];       /* [hypothesis][phase: 0 useOutofBoard, 1 not] solver iterations */
+  int32_t term[2][2];        /* termination: 0 max iterations, 1 gradient, 2 parameter, 3 function tol., 4 radius, 5 invalid */
+  int32_t n_evals[2];        /* residual evaluations actually executed per hypothesis */
+  float plane[4];            /* refined plane a,b,c,d */
+  float pca[16];             /* pca_matrix, row-major 4x4 (:347-349) */
+  float eigvals[3];          /* eigenValuesPCA (:339) */
+  double hist_min, hist_max, hist_mean, r_low, r_high; /* calHist (:256, :300) */
+  double gray[2];            /* gray_zone (:322-323) */
+  double theta_t[2][3];      /* per hypothesis: theta, t_y, t_z */
+  double cost[2];            /* per hypothesis: final Huber cost of the second phase */
+} ilcc2_diag;
+
+typedef struct ilcc2_handle ilcc2_handle;
+
+int ilcc2_version(void);
+void ilcc2_default_params(ilcc2_params* p);
+
+/* Reads grid_length / corner_in_x / corner_in_y from an OpenCV-YAML file the way
+ * LidarCornersEst::set_chessboard_param does (LidarCornersEst.cpp:20-46) and fills
+ * p->grid_length, p->cells_x <= p->cells_y. Other fields of *p are left untouched. */
+int ilcc2_set_chessboard_param(ilcc2_params* p, const char* cam_yaml_path);
+
+/* Creates a handle that owns all device scratch for up to max_frames frames of up to
+ * max_points_per_frame points each (no allocation happens per call afterwards).
+ * One handle per (GPU, stream); a handle is not thread-safe. */
+int ilcc2_create(const ilcc2_params* params, int device, int max_frames, int max_points_per_frame,
+                 ilcc2_handle** out);
+int ilcc2_destroy(ilcc2_handle* h);
+
+/* Last error text of the handle (or of the last failed ilcc2_create when h == NULL). */
+const char* ilcc2_last_error(const ilcc2_handle* h);
+
+/* The hot path for a batch of frames: replaces setROI + EuclideanCluster + PCA + get_corners.
+ *   points        n_frames frames of point records, back to back.  A record is `point_step` bytes with
+ *                 float32 x, y, z, intensity at byte offsets off_x/off_y/off_z/off_intensity:
+ *                 (16; 0,4,8,12) = packed XYZI float4;  (32; 0,4,8,16) = pcl::PointXYZI and the velodyne
+ *                 PointCloud2 records of the bundled bags (zero-copy from msg.data).
+ *   frame_offsets NULL -> every frame has points_per_frame records.  Else n_frames+1 record offsets (host
+ *                 memory, int64) so frames may have different sizes; points_per_frame is then ignored.
+ *   click_xyz     [n_frames][3] float32: /clicked_point per frame (get_lidar_corners.cpp:38-50).
+ *   flags         NULL (-> default_flags for all frames) or [n_frames] uint8 of ILCC2_FLAG_*.
+ *   plane_index_delta NULL or [n_frames] int8: net 'w' (+) / 's' (-) presses (Visualization.cpp:22-29).
+ *   corners_out   [n_frames][(cells_x-1)*(cells_y-1)][3] float32, LiDAR frame, reference lattice order
+ *                 (LidarCornersEst.cpp:524-534); NaN when status != ILCC2_OK.
+ *   status_out    [n_frames] int32 ILCC2_OK...
+ *   diag_out      NULL or [n_frames] ilcc2_diag.
+ *   stream        cudaStream_t (NULL = default stream).
+ * mem_kind says where points / click_xyz / flags / plane_index_delta / *_out live. */
+int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int points_per_frame,
+                          const int64_t* frame_offsets, int point_step, int off_x, int off_y, int off_z,
+                          int off_intensity, int mem_kind, const float* click_xyz, const uint8_t* flags,
+                          uint32_t default_flags, const int8_t* plane_index_delta, float* corners_out,
+                          int32_t* status_out, ilcc2_diag* diag_out, void* stream);
+
+/* Intermediate clouds of the LAST call for one frame, as the reference publishes them
+ * (m_cloud_ROI / cluster / m_cloud_chessboard; get_lidar_corners.cpp:192-201): original point indices
+ * into that frame, in input order.  which: 0 ROI, 1 chosen cluster, 2 chessboard plane.
+ * Synchronises the stream. Returns the count (<= cap entries written) or a negative error. */
+int ilcc2_fetch_indices(ilcc2_handle* h, int frame, int which, int32_t* out_host, int cap);
+
+/* Non-gray chessboard points in the PCA frame (m_cloud_PCA y,z + colour class) of the LAST call:
+ * yz_out [cap][2] float32, white_out [cap] uint8. Returns the count or a negative error. */
+int ilcc2_fetch_board_points(ilcc2_handle* h, int frame, float* yz_out_host, uint8_t* white_out_host, int cap);
+
+/* Per-kernel device times (ms, CUDA events on the call's stream) of the LAST call when profiling is on.
+ * names_out receives pointers to static strings. Returns the number of stages. */
+int ilcc2_set_profiling(ilcc2_handle* h, int enabled);
+int ilcc2_stage_times(ilcc2_handle* h, float* ms_out, const char** names_out, int cap);
+
+/* Kernels launched by this handle since creation (bench.py's gpu_launches). */
+int64_t ilcc2_launch_count(const ilcc2_handle* h);
+
+/* Output contract: process_data/<camera_name>_lidar_<bag_idx>.txt, "x y z\n" per corner with the default
+ * ostream precision of 6 significant digits (get_lidar_corners.cpp:27-36). */
+int ilcc2_save_corners2txt(const float* corners_xyz, int n_corners, const char* path);
+
+/* Frame sharding across ranks (one process per GPU): contiguous blocks. */
+void ilcc2_shard_range(int n_frames, int world_size, int rank, int* begin, int* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ILCC2_B200_H_ */

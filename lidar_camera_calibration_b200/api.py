@@ -1,0 +1,303 @@
+"""Host-side mirror of the reference's interface for the LiDAR corner path, over the C ABI.
+
+Two layers:
+  * CornerExtractor      -- thin wrapper of ilcc2_create / ilcc2_extract_corners for batches (numpy host arrays or
+                            torch CUDA tensors).  This is what bench.py and the parity tests call.
+  * LidarCornersEst      -- same method names, argument meaning and return values as the reference class
+                            (ilcc2/include/ilcc2/LidarCornersEst.h:40-67) as driven by ilcc2/test/get_lidar_corners.cpp:183-198:
+                            set_chessboard_param(yaml) / setROI(cloud, point) / EuclideanCluster() / PCA() /
+                            get_corners(corners); the GUI key presses become constructor/call arguments.
+All arithmetic happens in libilcc2_b200.so on the GPU; nothing here computes corners.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Diag, Params
+
+FLAG_TOPLEFT_WHITE = 1
+FLAG_INVERSE = 2
+FLAG_AUTO = 4
+MEM_HOST, MEM_DEVICE = 0, 1
+STATUS_NAMES = {0: "OK", 1: "NO_POINTS_IN_ROI", 2: "NO_CLUSTER", 3: "PLANE_TOO_SMALL",
+                4: "DEGENERATE_INTENSITY", 5: "NO_OPT_POINTS", 6: "RANSAC_FAILED"}
+STAGES = ("roi_filter", "cluster", "plane", "pca_gray", "board_fit")
+
+
+class Ilcc2Error(RuntimeError):
+    pass
+
+
+def default_params(**overrides) -> Params:
+    p = Params()
+    _lib.load().ilcc2_default_params(C.byref(p))
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def set_chessboard_param(p: Params, cam_yaml: str) -> bool:
+    """LidarCornersEst::set_chessboard_param (LidarCornersEst.cpp:20-46): grid_length and sorted (cells_x, cells_y)."""
+    return _lib.load().ilcc2_set_chessboard_param(C.byref(p), cam_yaml.encode()) == 0
+
+
+def diag_to_dict(d: Diag) -> dict:
+    out = {}
+    for name, _ in Diag._fields_:
+        v = getattr(d, name)
+        out[name] = np.ctypeslib.as_array(v).copy() if hasattr(v, "_length_") else v
+    return out
+
+
+def _layout(width: int):
+    if width == 4:
+        return 16, 0, 4, 8, 12
+    if width == 8:
+        return 32, 0, 4, 8, 16
+    raise ValueError("points must have 4 (packed XYZI) or 8 (32-byte PointCloud2 record) float32 columns")
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class CornerExtractor:
+    """Owns one ilcc2_handle (device scratch for max_frames x max_points_per_frame)."""
+
+    def __init__(self, max_frames: int, max_points_per_frame: int, params: Params | None = None, device: int = 0):
+        self._L = _lib.load()
+        self.params = params or default_params()
+        self.device = device
+        self.max_frames = max_frames
+        self.max_points = max_points_per_frame
+        self.n_corners = (self.params.cells_x - 1) * (self.params.cells_y - 1)
+        h = C.c_void_p()
+        rc = self._L.ilcc2_create(C.byref(self.params), device, max_frames, max_points_per_frame, C.byref(h))
+        if rc != 0:
+            raise Ilcc2Error(f"ilcc2_create failed ({rc}): {self._L.ilcc2_last_error(None).decode()}")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ilcc2_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise Ilcc2Error(f"ilcc2 error {rc}: {self._L.ilcc2_last_error(self._h).decode()}")
+
+    # ---- batch call, host buffers (numpy) ----
+    def extract(self, points: np.ndarray, clicks: np.ndarray, flags=FLAG_AUTO, plane_index_delta=None,
+                frame_offsets=None, want_diag: bool = False):
+        """points: (F, N, 4|8) float32, or (total, 4|8) with frame_offsets (F+1 int64). clicks (F,3).
+        flags: scalar applied to all frames, or (F,) uint8. Returns (status[F], corners[F,ncorn,3][, diags])."""
+        assert points.dtype == np.float32 and points.flags.c_contiguous
+        if frame_offsets is None:
+            assert points.ndim == 3
+            F, N, wdt = points.shape
+            fo_ptr = None
+        else:
+            assert points.ndim == 2
+            frame_offsets = np.ascontiguousarray(frame_offsets, np.int64)
+            F, N, wdt = frame_offsets.size - 1, 0, points.shape[1]
+            fo_ptr = frame_offsets.ctypes.data
+        step, ox, oy, oz, oi = _layout(wdt)
+        clicks = np.ascontiguousarray(clicks, np.float32).reshape(F, 3)
+        corners = np.empty((F, self.n_corners, 3), np.float32)
+        status = np.empty(F, np.int32)
+        diags = (Diag * F)() if want_diag else None
+        fl_ptr, dflt = None, 0
+        if np.isscalar(flags):
+            dflt = int(flags)
+        else:
+            fl = np.ascontiguousarray(flags, np.uint8)
+            assert fl.size == F
+            fl_ptr = fl.ctypes.data
+        pd_ptr = None
+        if plane_index_delta is not None:
+            pd = np.ascontiguousarray(plane_index_delta, np.int8)
+            assert pd.size == F
+            pd_ptr = pd.ctypes.data
+        rc = self._L.ilcc2_extract_corners(self._h, points.ctypes.data, F, N, fo_ptr, step, ox, oy, oz, oi, MEM_HOST,
+                                           clicks.ctypes.data, fl_ptr, dflt, pd_ptr, corners.ctypes.data,
+                                           status.ctypes.data, C.cast(diags, C.c_void_p) if want_diag else None, None)
+        self._check(rc)
+        if want_diag:
+            return status, corners, [diag_to_dict(d) for d in diags]
+        return status, corners
+
+    # ---- batch call, raw pointers (pinned host or device), asynchronous for device memory ----
+    def extract_raw(self, points_ptr: int, n_frames: int, points_per_frame: int, width: int, clicks_ptr: int,
+                    corners_ptr: int, status_ptr: int, mem_kind: int, flags: int = FLAG_AUTO, stream: int = 0,
+                    flags_ptr: int = 0, diag_ptr: int = 0):
+        step, ox, oy, oz, oi = _layout(width)
+        rc = self._L.ilcc2_extract_corners(self._h, points_ptr, n_frames, points_per_frame, None, step, ox, oy, oz, oi,
+                                           mem_kind, clicks_ptr, flags_ptr or None, flags, None, corners_ptr,
+                                           status_ptr, diag_ptr or None, stream or None)
+        self._check(rc)
+
+    def extract_torch(self, points, clicks, corners=None, status=None, flags: int = FLAG_AUTO, stream=None):
+        """points: CUDA float32 tensor (F, N, 4|8); clicks CUDA (F,3). Asynchronous on `stream` (default: current)."""
+        import torch
+        assert points.is_cuda and points.dtype == torch.float32 and points.is_contiguous() and points.dim() == 3
+        F, N, wdt = points.shape
+        if corners is None:
+            corners = torch.empty((F, self.n_corners, 3), dtype=torch.float32, device=points.device)
+        if status is None:
+            status = torch.empty((F,), dtype=torch.int32, device=points.device)
+        st = stream if stream is not None else torch.cuda.current_stream(points.device)
+        self.extract_raw(points.data_ptr(), F, N, wdt, clicks.data_ptr(), corners.data_ptr(), status.data_ptr(),
+                         MEM_DEVICE, flags, st.cuda_stream)
+        return status, corners
+
+    # ---- introspection of the last call ----
+    def fetch_indices(self, frame: int, which: int) -> np.ndarray:
+        """which: 0 m_cloud_ROI, 1 chosen cluster, 2 m_cloud_chessboard -- original point indices of `frame`."""
+        buf = np.empty(self.max_points, np.int32)
+        n = self._L.ilcc2_fetch_indices(self._h, frame, which, buf.ctypes.data, buf.size)
+        if n < 0:
+            raise Ilcc2Error(f"ilcc2_fetch_indices failed ({n})")
+        return buf[:n].copy()
+
+    def fetch_board_points(self, frame: int):
+        yz = np.empty((self.max_points, 2), np.float32)
+        wh = np.empty(self.max_points, np.uint8)
+        n = self._L.ilcc2_fetch_board_points(self._h, frame, yz.ctypes.data, wh.ctypes.data, self.max_points)
+        if n < 0:
+            raise Ilcc2Error(f"ilcc2_fetch_board_points failed ({n})")
+        return yz[:n].copy(), wh[:n].copy()
+
+    def set_profiling(self, enabled: bool):
+        self._check(self._L.ilcc2_set_profiling(self._h, int(enabled)))
+
+    def stage_times(self) -> dict:
+        ms = (C.c_float * 8)()
+        names = (C.c_char_p * 8)()
+        n = self._L.ilcc2_stage_times(self._h, ms, names, 8)
+        if n < 0:
+            raise Ilcc2Error("ilcc2_stage_times failed")
+        return {names[i].decode(): float(ms[i]) for i in range(n)}
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.ilcc2_launch_count(self._h))
+
+
+def save_corners2txt(corners: np.ndarray, path: str):
+    """get_lidar_corners.cpp:27-36: 'x y z' per line, 6 significant digits."""
+    c = np.ascontiguousarray(corners, np.float32).reshape(-1, 3)
+    rc = _lib.load().ilcc2_save_corners2txt(c.ctypes.data, c.shape[0], path.encode())
+    if rc != 0:
+        raise Ilcc2Error(f"ilcc2_save_corners2txt({path}) failed ({rc})")
+
+
+def shard_range(n_frames: int, world_size: int, rank: int):
+    b, c = C.c_int(), C.c_int()
+    _lib.load().ilcc2_shard_range(n_frames, world_size, rank, C.byref(b), C.byref(c))
+    return b.value, c.value
+
+
+class LidarCornersEst:
+    """Drop-in shaped like the reference class; one frame at a time (what the ROS node does).
+
+    Key presses of the two PCL viewer windows become attributes set before the call:
+      plane_index_delta  net 'w'/'s' presses in EuclideanCluster()   (Visualization.cpp:22-29)
+      topleft_white      True = one press of 'd' in get_corners()     (Visualization.cpp:45-48)
+      inverse            True = one press of 'a'                      (Visualization.cpp:49-52)
+      auto               True = unattended colour-phase selection (not in the reference)
+    """
+
+    def __init__(self, device: int = 0, max_points: int = 150000):
+        self.params = default_params()
+        self._device = device
+        self._max_points = max_points
+        self._ex: CornerExtractor | None = None
+        self.plane_index_delta = 0
+        self.topleft_white = False
+        self.inverse = False
+        self.auto = False
+        self.m_click_point = None
+        self.m_cloud_ROI = np.empty((0, 4), np.float32)
+        self.m_cloud_chessboard = np.empty((0, 4), np.float32)
+        self.m_cloud_PCA = np.empty((0, 4), np.float32)
+        self.m_cloud_corners = np.empty((0, 3), np.float32)
+        self.pca_matrix = np.eye(4, dtype=np.float32)
+        self.m_gray_zone = np.zeros(2)
+        self.diag: dict | None = None
+        self._cloud = None
+        self._status = None
+        self._corners = None
+
+    # LidarCornersEst.cpp:20-46
+    def set_chessboard_param(self, cam_yaml: str) -> bool:
+        ok = set_chessboard_param(self.params, cam_yaml)
+        self._ex = None
+        return ok
+
+    @property
+    def m_grid_length(self):
+        return self.params.grid_length
+
+    @property
+    def m_grid_size(self):
+        return (self.params.cells_x, self.params.cells_y)
+
+    # LidarCornersEst.cpp:48-70.  cloud: (N,4) packed XYZI or (N,8) 32-byte records, float32
+    def setROI(self, cloud: np.ndarray, point) -> None:
+        self._cloud = np.ascontiguousarray(cloud, np.float32)
+        self.m_click_point = np.asarray(point, np.float32).reshape(3)
+        self._status = None
+
+    def _xyzi(self, idx):
+        c = self._cloud
+        return c[idx][:, [0, 1, 2, 3]] if c.shape[1] == 4 else c[idx][:, [0, 1, 2, 4]]
+
+    def _run(self):
+        if self._ex is None:
+            self._ex = CornerExtractor(1, self._max_points, self.params, self._device)
+        flags = (FLAG_AUTO if self.auto else 0) | (FLAG_TOPLEFT_WHITE if self.topleft_white else 0) | \
+                (FLAG_INVERSE if self.inverse else 0)
+        st, corners, diags = self._ex.extract(self._cloud[None], self.m_click_point[None], flags=flags,
+                                              plane_index_delta=[self.plane_index_delta], want_diag=True)
+        self._status, self._corners, self.diag = int(st[0]), corners[0], diags[0]
+        self.m_cloud_ROI = self._xyzi(self._ex.fetch_indices(0, 0))
+        self.m_cloud_chessboard = self._xyzi(self._ex.fetch_indices(0, 2))
+        self.pca_matrix = self.diag["pca"].reshape(4, 4)
+        self.m_gray_zone = self.diag["gray"]
+
+    # LidarCornersEst.cpp:124-186: True when a chessboard plane was found ('o' pressed)
+    def EuclideanCluster(self) -> bool:
+        if self._cloud is None:
+            raise Ilcc2Error("setROI() must be called first")
+        self._run()
+        return self._status not in (1, 2, 3, 6)
+
+    # LidarCornersEst.cpp:366-372
+    def PCA(self) -> None:
+        if self._status is None:
+            self._run()
+        if len(self.m_cloud_chessboard):
+            T = self.pca_matrix
+            xyz = self.m_cloud_chessboard[:, :3] @ T[:3, :3].T + T[:3, 3]
+            self.m_cloud_PCA = np.concatenate([xyz, self.m_cloud_chessboard[:, 3:4]], 1).astype(np.float32)
+
+    # LidarCornersEst.cpp:374-450: fills `corners` (list) with (x,y,z) tuples; True when accepted ('k')
+    def get_corners(self, corners: list) -> bool:
+        if self._status is None:
+            self._run()
+        if self._status != 0:
+            return False
+        self.m_cloud_corners = self._corners.copy()
+        corners.extend([tuple(float(v) for v in c) for c in self._corners])
+        return True

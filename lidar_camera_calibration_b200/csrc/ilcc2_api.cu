@@ -1,0 +1,501 @@
+// ilcc2_api.cu -- host side of the C ABI declared in include/ilcc2_b200.h.
+// Owns the handle (device scratch sized once at creation), validates arguments, stages host buffers,
+// launches the five stage kernels on the caller's stream and returns results.  No CPU compute path exists:
+// every compute entry point fails loudly when CUDA is unavailable.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "ilcc2_internal.h"
+
+using namespace ilcc2;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int kStages = 5;
+const char* kStageNames[kStages] = {"roi_filter", "cluster", "plane", "pca_gray", "board_fit"};
+
+}  // namespace
+
+struct ilcc2_handle {
+  ilcc2_params params;
+  DevParams dp;
+  int device = 0;
+  int max_frames = 0;
+  int max_points = 0;
+  int cap = 0;
+  Workspace ws{};
+  // owned device memory
+  std::vector<void*> allocs;
+  unsigned char* d_points_stage = nullptr;
+  size_t points_stage_bytes = 0;
+  float* d_clicks = nullptr;
+  uint8_t* d_flags = nullptr;
+  int8_t* d_pdelta = nullptr;
+  long long* d_frame_off = nullptr;
+  float* d_corners = nullptr;
+  int32_t* d_status = nullptr;
+  ilcc2_diag* d_diag = nullptr;
+  uint32_t* d_rnd = nullptr;
+  // last call
+  int last_n_frames = 0;
+  std::vector<long long> last_frame_off;  // host copy (empty when fixed size)
+  int last_ppf = 0;
+  cudaStream_t last_stream = nullptr;
+  // profiling
+  bool profiling = false;
+  cudaEvent_t ev[kStages + 1] = {};
+  bool ev_valid = false;
+  int64_t launches = 0;
+  std::string error;
+};
+
+namespace {
+
+int fail(ilcc2_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h)
+    h->error = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define CU_TRY(h, expr)                                                                              \
+  do {                                                                                               \
+    cudaError_t e__ = (expr);                                                                        \
+    if (e__ != cudaSuccess) return fail(h, ILCC2_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(ilcc2_handle* h, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T) > 0 ? count * sizeof(T) : 1);
+  if (e == cudaSuccess) {
+    h->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+  }
+  return e;
+}
+
+bool params_valid(const ilcc2_params& p) {
+  return p.roi_half_x > 0 && p.roi_half_y > 0 && p.roi_half_z > 0 && p.cluster_tolerance > 0 &&
+         p.min_cluster_size >= 1 && p.max_cluster_size >= p.min_cluster_size && p.ransac_threshold > 0 &&
+         p.ransac_max_iterations >= 1 && p.ransac_probability > 0 && p.ransac_probability < 1 && p.hist_bins >= 1 &&
+         p.hist_bins <= 4096 && p.gray_rate > 1 && p.huber_delta > 0 && p.grid_length > 0 && p.cells_x >= 2 &&
+         p.cells_y >= 2 && p.max_solver_iterations >= 1;
+}
+
+void derive(const ilcc2_params& p, DevParams& d) {
+  d.roi_hx = p.roi_half_x;
+  d.roi_hy = p.roi_half_y;
+  d.roi_hz = p.roi_half_z;
+  d.tol2 = (float)((double)p.cluster_tolerance * (double)p.cluster_tolerance);
+  d.cell = (float)(0.95 * (double)p.cluster_tolerance / std::sqrt(3.0));
+  d.ncx = (int)std::floor(2.0 * p.roi_half_x / d.cell) + 2;
+  d.ncy = (int)std::floor(2.0 * p.roi_half_y / d.cell) + 2;
+  d.ncz = (int)std::floor(2.0 * p.roi_half_z / d.cell) + 2;
+  d.min_cl = p.min_cluster_size;
+  d.max_cl = p.max_cluster_size;
+  d.ransac_thr = p.ransac_threshold;
+  d.ransac_max_iter = p.ransac_max_iterations;
+  d.ransac_log_prob = std::log(1.0 - p.ransac_probability);
+  d.hist_bins = p.hist_bins;
+  d.gray_rate = p.gray_rate;
+  d.huber_a = p.huber_delta;
+  d.huber_b = p.huber_delta * p.huber_delta;
+  d.g = p.grid_length;
+  d.inv_g = 1.0 / p.grid_length;
+  d.W = p.cells_x;
+  d.H = p.cells_y;
+  d.wg2 = (double)p.cells_x * p.grid_length / 2.0;
+  d.hg2 = (double)p.cells_y * p.grid_length / 2.0;
+  d.min_board = p.min_board_points;
+  d.max_solver_iter = p.max_solver_iterations;
+  d.ncorners = (p.cells_x - 1) * (p.cells_y - 1);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ilcc2_version(void) { return ILCC2_VERSION; }
+
+void ilcc2_default_params(ilcc2_params* p) {
+  if (!p) return;
+  p->roi_half_x = 1.0f;
+  p->roi_half_y = 1.5f;
+  p->roi_half_z = 2.0f;
+  p->cluster_tolerance = 0.12f;
+  p->min_cluster_size = 100;
+  p->max_cluster_size = 25000;
+  p->ransac_threshold = 0.03;
+  p->ransac_max_iterations = 50;
+  p->ransac_probability = 0.99;
+  p->hist_bins = 100;
+  p->gray_rate = 2.5;
+  p->huber_delta = 0.1;
+  p->grid_length = 0.15;
+  p->cells_x = 6;
+  p->cells_y = 8;
+  p->min_board_points = 0;
+  p->max_solver_iterations = 50;
+}
+
+int ilcc2_set_chessboard_param(ilcc2_params* p, const char* cam_yaml_path) {
+  if (!p || !cam_yaml_path) return fail(nullptr, ILCC2_ERR_INVALID_ARGUMENT, "null argument");
+  std::ifstream in(cam_yaml_path);
+  if (!in.is_open()) return fail(nullptr, ILCC2_ERR_IO, "can not open %s", cam_yaml_path);
+  double grid = -1.0;
+  int cx = -1, cy = -1;
+  std::string line;
+  while (std::getline(in, line)) {
+    const size_t c = line.find(':');
+    if (c == std::string::npos) continue;
+    std::string key = line.substr(0, c);
+    key.erase(0, key.find_first_not_of(" \t"));
+    key.erase(key.find_last_not_of(" \t") + 1);
+    const std::string val = line.substr(c + 1);
+    if (key == "grid_length") grid = atof(val.c_str());
+    if (key == "corner_in_x") cx = atoi(val.c_str());
+    if (key == "corner_in_y") cy = atoi(val.c_str());
+  }
+  if (!(grid > 0) || cx < 1 || cy < 1)
+    return fail(nullptr, ILCC2_ERR_IO, "%s: grid_length / corner_in_x / corner_in_y missing", cam_yaml_path);
+  p->grid_length = grid;
+  int a = cx + 1, b = cy + 1;  // LidarCornersEst.cpp:31-39
+  if (a > b) std::swap(a, b);
+  p->cells_x = a;
+  p->cells_y = b;
+  return ILCC2_SUCCESS;
+}
+
+int ilcc2_create(const ilcc2_params* params, int device, int max_frames, int max_points_per_frame,
+                 ilcc2_handle** out) {
+  if (!out) return fail(nullptr, ILCC2_ERR_INVALID_ARGUMENT, "out is null");
+  *out = nullptr;
+  if (max_frames < 1 || max_points_per_frame < 1)
+    return fail(nullptr, ILCC2_ERR_INVALID_ARGUMENT, "max_frames and max_points_per_frame must be >= 1");
+  ilcc2_params p;
+  if (params)
+    p = *params;
+  else
+    ilcc2_default_params(&p);
+  if (!params_valid(p)) return fail(nullptr, ILCC2_ERR_INVALID_ARGUMENT, "invalid ilcc2_params");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, ILCC2_ERR_CUDA, "no CUDA device (%s); this library has no CPU path",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= ndev) return fail(nullptr, ILCC2_ERR_INVALID_ARGUMENT, "device %d out of range", device);
+  CU_TRY(nullptr, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, ILCC2_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+
+  ilcc2_handle* h = new ilcc2_handle();
+  h->params = p;
+  derive(p, h->dp);
+  if ((long long)h->dp.ncx * h->dp.ncy * h->dp.ncz >= (1ll << 31)) {
+    delete h;
+    return fail(nullptr, ILCC2_ERR_INVALID_ARGUMENT, "ROI / cluster_tolerance give too many hash cells");
+  }
+  h->device = device;
+  h->max_frames = max_frames;
+  h->max_points = max_points_per_frame;
+  h->cap = max_points_per_frame;
+  const size_t F = (size_t)max_frames, R = (size_t)h->cap;
+  Workspace& w = h->ws;
+  int ts = 1;
+  while (ts < 2 * h->cap) ts <<= 1;
+  w.cl_ts = ts;
+  w.cl_stride = 2ll * ts + 3ll * h->cap;
+  const bool need_global_cluster = h->cap > kClusterSmemPts;
+  cudaError_t ce = cudaSuccess;
+  auto A = [&](cudaError_t r) { if (ce == cudaSuccess) ce = r; };
+  A(dev_alloc(h, &w.roi_pts, F * R));
+  A(dev_alloc(h, &w.roi_src, F * R));
+  A(dev_alloc(h, &w.roi_count, F));
+  A(dev_alloc(h, &w.nn_key, F));
+  A(dev_alloc(h, &w.sel_idx, F * R));
+  A(dev_alloc(h, &w.sel_count, F));
+  A(dev_alloc(h, &w.brd_idx, F * R));
+  A(dev_alloc(h, &w.brd_count, F));
+  A(dev_alloc(h, &w.tmp_idx, F * R));
+  A(dev_alloc(h, &w.cl_scratch, need_global_cluster ? F * (size_t)w.cl_stride : 1));
+  A(dev_alloc(h, &w.opt_yz, F * R));
+  A(dev_alloc(h, &w.opt_white, F * R));
+  A(dev_alloc(h, &w.opt_count, F));
+  A(dev_alloc(h, &h->d_clicks, F * 3));
+  A(dev_alloc(h, &h->d_flags, F));
+  A(dev_alloc(h, &h->d_pdelta, F));
+  A(dev_alloc(h, &h->d_frame_off, F + 1));
+  A(dev_alloc(h, &h->d_corners, F * (size_t)h->dp.ncorners * 3));
+  A(dev_alloc(h, &h->d_status, F));
+  A(dev_alloc(h, &h->d_diag, F));
+  A(dev_alloc(h, &h->d_rnd, (size_t)kRndTable));
+  if (ce == cudaSuccess) {
+    // PCL SampleConsensusModel draws: boost::mt19937 seeded 12345 through uniform_int<>(0, INT_MAX) = mt() >> 1
+    std::vector<uint32_t> tab(kRndTable);
+    std::mt19937 gen(12345u);
+    for (int k = 0; k < kRndTable; ++k) tab[k] = (uint32_t)gen() >> 1;
+    A(cudaMemcpy(h->d_rnd, tab.data(), sizeof(uint32_t) * kRndTable, cudaMemcpyHostToDevice));
+  }
+  if (ce == cudaSuccess) A(configure_kernels());
+  for (int i = 0; i <= kStages && ce == cudaSuccess; ++i) A(cudaEventCreate(&h->ev[i]));
+  if (ce != cudaSuccess) {
+    const int rc = fail(nullptr, ILCC2_ERR_CUDA, "ilcc2_create: %s", cudaGetErrorString(ce));
+    for (void* q : h->allocs) cudaFree(q);
+    delete h;
+    return rc;
+  }
+  w.rnd_table = h->d_rnd;
+  w.cap = h->cap;
+  *out = h;
+  return ILCC2_SUCCESS;
+}
+
+int ilcc2_destroy(ilcc2_handle* h) {
+  if (!h) return ILCC2_SUCCESS;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* q : h->allocs) cudaFree(q);
+  if (h->d_points_stage) cudaFree(h->d_points_stage);
+  for (int i = 0; i <= kStages; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  delete h;
+  return ILCC2_SUCCESS;
+}
+
+const char* ilcc2_last_error(const ilcc2_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int points_per_frame,
+                          const int64_t* frame_offsets, int point_step, int off_x, int off_y, int off_z,
+                          int off_intensity, int mem_kind, const float* click_xyz, const uint8_t* flags,
+                          uint32_t default_flags, const int8_t* plane_index_delta, float* corners_out,
+                          int32_t* status_out, ilcc2_diag* diag_out, void* stream) {
+  if (!h) return ILCC2_ERR_INVALID_ARGUMENT;
+  if (n_frames == 0) return ILCC2_SUCCESS;
+  if (!points || !click_xyz || !corners_out || !status_out)
+    return fail(h, ILCC2_ERR_INVALID_ARGUMENT, "points, click_xyz, corners_out and status_out are required");
+  if (n_frames < 0 || n_frames > h->max_frames)
+    return fail(h, ILCC2_ERR_CAPACITY, "n_frames %d exceeds handle capacity %d", n_frames, h->max_frames);
+  if (mem_kind != ILCC2_MEM_HOST && mem_kind != ILCC2_MEM_DEVICE)
+    return fail(h, ILCC2_ERR_INVALID_ARGUMENT, "mem_kind must be ILCC2_MEM_HOST or ILCC2_MEM_DEVICE");
+  if (point_step < 16 || point_step % 4 != 0) return fail(h, ILCC2_ERR_INVALID_ARGUMENT, "point_step must be a multiple of 4, >= 16");
+  const int offs[4] = {off_x, off_y, off_z, off_intensity};
+  for (int o : offs)
+    if (o < 0 || o % 4 != 0 || o + 4 > point_step) return fail(h, ILCC2_ERR_INVALID_ARGUMENT, "field offset %d invalid", o);
+  const bool fast = (point_step == 16 && off_x == 0 && off_y == 4 && off_z == 8 && off_intensity == 12) ||
+                    (point_step == 32 && off_x == 0 && off_y == 4 && off_z == 8 && off_intensity == 16);
+  long long total_points = 0;
+  h->last_frame_off.clear();
+  if (frame_offsets) {
+    for (int f = 0; f < n_frames; ++f) {
+      const long long n = frame_offsets[f + 1] - frame_offsets[f];
+      if (n < 0 || n > h->max_points)
+        return fail(h, ILCC2_ERR_CAPACITY, "frame %d has %lld points; handle capacity %d", f, n, h->max_points);
+    }
+    if (frame_offsets[0] != 0) return fail(h, ILCC2_ERR_INVALID_ARGUMENT, "frame_offsets[0] must be 0");
+    total_points = frame_offsets[n_frames];
+    h->last_frame_off.assign(frame_offsets, frame_offsets + n_frames + 1);
+  } else {
+    if (points_per_frame < 0 || points_per_frame > h->max_points)
+      return fail(h, ILCC2_ERR_CAPACITY, "points_per_frame %d exceeds handle capacity %d", points_per_frame, h->max_points);
+    total_points = (long long)n_frames * points_per_frame;
+  }
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Workspace w = h->ws;
+  const size_t bytes = (size_t)total_points * point_step;
+  if (mem_kind == ILCC2_MEM_HOST) {
+    if (bytes > h->points_stage_bytes) {
+      if (h->d_points_stage) cudaFree(h->d_points_stage);
+      h->d_points_stage = nullptr;
+      h->points_stage_bytes = 0;
+      const size_t want = (size_t)h->max_frames * h->max_points * point_step;
+      CU_TRY(h, cudaMalloc(&h->d_points_stage, want > bytes ? want : bytes));
+      h->points_stage_bytes = want > bytes ? want : bytes;
+    }
+    CU_TRY(h, cudaMemcpyAsync(h->d_points_stage, points, bytes, cudaMemcpyHostToDevice, s));
+    CU_TRY(h, cudaMemcpyAsync(h->d_clicks, click_xyz, sizeof(float) * 3 * n_frames, cudaMemcpyHostToDevice, s));
+    if (flags) CU_TRY(h, cudaMemcpyAsync(h->d_flags, flags, n_frames, cudaMemcpyHostToDevice, s));
+    if (plane_index_delta) CU_TRY(h, cudaMemcpyAsync(h->d_pdelta, plane_index_delta, n_frames, cudaMemcpyHostToDevice, s));
+    w.points = h->d_points_stage;
+    w.clicks = h->d_clicks;
+    w.flags = flags ? h->d_flags : nullptr;
+    w.pdelta = plane_index_delta ? h->d_pdelta : nullptr;
+    w.corners = h->d_corners;
+    w.status = h->d_status;
+  } else {
+    if ((reinterpret_cast<uintptr_t>(points) & 15u) != 0 && fast)
+      return fail(h, ILCC2_ERR_INVALID_ARGUMENT, "device points must be 16-byte aligned");
+    w.points = static_cast<const unsigned char*>(points);
+    w.clicks = click_xyz;
+    w.flags = flags;
+    w.pdelta = plane_index_delta;
+    w.corners = corners_out;
+    w.status = status_out;
+  }
+  if (frame_offsets) {
+    CU_TRY(h, cudaMemcpyAsync(h->d_frame_off, frame_offsets, sizeof(long long) * (n_frames + 1), cudaMemcpyHostToDevice, s));
+    w.frame_off = h->d_frame_off;
+  } else {
+    w.frame_off = nullptr;
+  }
+  w.pts_per_frame = points_per_frame;
+  w.step = point_step;
+  w.ox = off_x;
+  w.oy = off_y;
+  w.oz = off_z;
+  w.oi = off_intensity;
+  w.default_flags = default_flags;
+  w.n_frames = n_frames;
+  w.diag = h->d_diag;
+  CU_TRY(h, cudaMemsetAsync(h->d_diag, 0, sizeof(ilcc2_diag) * n_frames, s));
+
+  const bool prof = h->profiling;
+  static const bool debug_sync = getenv("ILCC2_DEBUG_SYNC") != nullptr;  // debugging aid: sync + report per stage
+  auto stage_done = [&](int i) -> cudaError_t {
+    if (prof) {
+      cudaError_t e = cudaEventRecord(h->ev[i], s);
+      if (e != cudaSuccess) return e;
+    }
+    if (debug_sync && i > 0) {
+      cudaError_t e = cudaStreamSynchronize(s);
+      fprintf(stderr, "[ilcc2] stage %s done: %s\n", kStageNames[i - 1], cudaGetErrorString(e));
+      fflush(stderr);
+      return e;
+    }
+    return cudaSuccess;
+  };
+  CU_TRY(h, stage_done(0));
+  launch_roi_filter(w, h->dp, s);
+  CU_TRY(h, stage_done(1));
+  launch_cluster(w, h->dp, s);
+  CU_TRY(h, stage_done(2));
+  launch_plane(w, h->dp, s);
+  CU_TRY(h, stage_done(3));
+  launch_pca_gray(w, h->dp, s);
+  CU_TRY(h, stage_done(4));
+  launch_board_fit(w, h->dp, s);
+  CU_TRY(h, stage_done(5));
+  h->ev_valid = prof;
+  h->launches += kStages;
+  CU_TRY(h, cudaGetLastError());
+
+  h->last_n_frames = n_frames;
+  h->last_ppf = points_per_frame;
+  h->last_stream = s;
+  const size_t cbytes = sizeof(float) * 3 * (size_t)h->dp.ncorners * n_frames;
+  if (mem_kind == ILCC2_MEM_HOST) {
+    CU_TRY(h, cudaMemcpyAsync(corners_out, h->d_corners, cbytes, cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaMemcpyAsync(status_out, h->d_status, sizeof(int32_t) * n_frames, cudaMemcpyDeviceToHost, s));
+    if (diag_out) CU_TRY(h, cudaMemcpyAsync(diag_out, h->d_diag, sizeof(ilcc2_diag) * n_frames, cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaStreamSynchronize(s));
+  } else if (diag_out) {
+    CU_TRY(h, cudaMemcpyAsync(diag_out, h->d_diag, sizeof(ilcc2_diag) * n_frames, cudaMemcpyDeviceToDevice, s));
+  }
+  return ILCC2_SUCCESS;
+}
+
+int ilcc2_fetch_indices(ilcc2_handle* h, int frame, int which, int32_t* out_host, int cap) {
+  if (!h || !out_host || frame < 0 || frame >= h->last_n_frames || which < 0 || which > 2) return -ILCC2_ERR_INVALID_ARGUMENT;
+  if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->last_stream) != cudaSuccess) return -ILCC2_ERR_CUDA;
+  const Workspace& w = h->ws;
+  const size_t R = (size_t)h->cap;
+  int n = 0;
+  const int* cnt = which == 0 ? w.roi_count : which == 1 ? w.sel_count : w.brd_count;
+  if (cudaMemcpy(&n, cnt + frame, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -ILCC2_ERR_CUDA;
+  if (n <= 0) return 0;
+  const int m = n < cap ? n : cap;
+  std::vector<int> src(R), idx;
+  int nroi = 0;
+  cudaMemcpy(&nroi, w.roi_count + frame, sizeof(int), cudaMemcpyDeviceToHost);
+  if (cudaMemcpy(src.data(), w.roi_src + frame * R, sizeof(int) * (size_t)nroi, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -ILCC2_ERR_CUDA;
+  if (which == 0) {
+    for (int i = 0; i < m; ++i) out_host[i] = src[i];
+    return n;
+  }
+  idx.resize(n);
+  const int* list = which == 1 ? w.sel_idx : w.brd_idx;
+  if (cudaMemcpy(idx.data(), list + frame * R, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -ILCC2_ERR_CUDA;
+  for (int i = 0; i < m; ++i) out_host[i] = src[idx[i]];
+  return n;
+}
+
+int ilcc2_fetch_board_points(ilcc2_handle* h, int frame, float* yz_out_host, uint8_t* white_out_host, int cap) {
+  if (!h || !yz_out_host || !white_out_host || frame < 0 || frame >= h->last_n_frames) return -ILCC2_ERR_INVALID_ARGUMENT;
+  if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->last_stream) != cudaSuccess) return -ILCC2_ERR_CUDA;
+  const Workspace& w = h->ws;
+  const size_t R = (size_t)h->cap;
+  int n = 0;
+  if (cudaMemcpy(&n, w.opt_count + frame, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -ILCC2_ERR_CUDA;
+  const int m = n < cap ? n : cap;
+  if (m > 0) {
+    if (cudaMemcpy(yz_out_host, w.opt_yz + frame * R, sizeof(float2) * (size_t)m, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(white_out_host, w.opt_white + frame * R, (size_t)m, cudaMemcpyDeviceToHost) != cudaSuccess)
+      return -ILCC2_ERR_CUDA;
+  }
+  return n;
+}
+
+int ilcc2_set_profiling(ilcc2_handle* h, int enabled) {
+  if (!h) return ILCC2_ERR_INVALID_ARGUMENT;
+  h->profiling = enabled != 0;
+  return ILCC2_SUCCESS;
+}
+
+int ilcc2_stage_times(ilcc2_handle* h, float* ms_out, const char** names_out, int cap) {
+  if (!h) return -ILCC2_ERR_INVALID_ARGUMENT;
+  if (!h->ev_valid) return 0;
+  if (cudaSetDevice(h->device) != cudaSuccess || cudaEventSynchronize(h->ev[kStages]) != cudaSuccess) return -ILCC2_ERR_CUDA;
+  for (int i = 0; i < kStages && i < cap; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]);
+    if (ms_out) ms_out[i] = ms;
+    if (names_out) names_out[i] = kStageNames[i];
+  }
+  return kStages;
+}
+
+int64_t ilcc2_launch_count(const ilcc2_handle* h) { return h ? h->launches : 0; }
+
+int ilcc2_save_corners2txt(const float* corners_xyz, int n_corners, const char* path) {
+  if (!corners_xyz || !path || n_corners < 0) return ILCC2_ERR_INVALID_ARGUMENT;
+  std::ofstream out(path, std::ios_base::trunc);
+  if (!out.is_open()) return ILCC2_ERR_IO;
+  for (int i = 0; i < n_corners; ++i)
+    out << corners_xyz[3 * i] << " " << corners_xyz[3 * i + 1] << " " << corners_xyz[3 * i + 2] << std::endl;
+  out.close();
+  return out.fail() ? ILCC2_ERR_IO : ILCC2_SUCCESS;
+}
+
+void ilcc2_shard_range(int n_frames, int world_size, int rank, int* begin, int* count) {
+  if (world_size < 1) world_size = 1;
+  const long long b = (long long)n_frames * rank / world_size;
+  const long long e = (long long)n_frames * (rank + 1) / world_size;
+  if (begin) *begin = (int)b;
+  if (count) *count = (int)(e - b);
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+// Internal declarations shared by the kernels (ilcc2_kernels.cu) and the C-ABI host code (ilcc2_api.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ilcc2_b200.h"
+
+namespace ilcc2 {
+
+// Kernel-side copy of ilcc2_params plus derived constants (computed once on the host, in double).
+struct DevParams {
+  float roi_hx, roi_hy, roi_hz;
+  float tol2;            // (float)(tol*tol): FLANN radius search compares squared distances
+  float cell;            // cluster hash cell edge = 0.95 * tol / sqrt(3): same cell => linked
+  int ncx, ncy, ncz;     // cells per axis over the ROI box
+  int min_cl, max_cl;
+  double ransac_thr;
+  int ransac_max_iter;
+  double ransac_log_prob;
+  int hist_bins;
+  double gray_rate;
+  double huber_a, huber_b;
+  double g, inv_g, wg2, hg2;
+  int W, H;
+  int min_board;
+  int max_solver_iter;
+  int ncorners;
+};
+
+constexpr int kRoiThreads = 512;      // K1 CTA size
+constexpr int kRoiUnroll = 4;         // K1 records per thread per tile
+constexpr int kClusterThreads = 256;  // K2 CTA size
+constexpr int kClusterSmemPts = 4096; // K2: frames with at most this many ROI points cluster in shared memory
+constexpr int kClusterSmemSlots = 8192;
+constexpr int kPlaneThreads = 128;    // K3/K4 CTA size == canonical reduction width of their double sums
+constexpr int kFitThreads = 64;       // K5: warp 0 = hypothesis topleftWhite=false, warp 1 = true
+constexpr int kFitSmemPts = 4096;     // K5: board points staged in shared memory up to this count
+constexpr int kRndTable = 8192;       // PCL RANSAC draw table length
+
+// Everything a launch needs; passed by value.
+struct Workspace {
+  // caller input (device pointers)
+  const unsigned char* points;
+  const long long* frame_off;  // nullable
+  int pts_per_frame;
+  int step, ox, oy, oz, oi;
+  const float* clicks;
+  const uint8_t* flags;        // nullable
+  uint32_t default_flags;
+  const int8_t* pdelta;        // nullable
+  int n_frames;
+  int cap;                     // per-frame capacity R of the ROI-sized arrays
+  // scratch
+  float4* roi_pts;             // [F][R] ROI points (x,y,z,intensity), input order
+  int* roi_src;                // [F][R] original index of each ROI point
+  int* roi_count;              // [F]
+  unsigned long long* nn_key;  // [F] (dist2 bits << 32 | ROI index) of the click's nearest neighbour
+  int* sel_idx;                // [F][R] chosen cluster, ROI indices ascending
+  int* sel_count;              // [F]
+  int* brd_idx;                // [F][R] plane inliers, ROI indices ascending
+  int* brd_count;              // [F]
+  int* tmp_idx;                // [F][R] RANSAC permutation, then inliers of the sample model
+  int* cl_scratch;             // [F][cl_stride] global-memory clustering tables for large ROIs
+  int cl_ts;                   // slots in the global hash table (power of two)
+  long long cl_stride;
+  float2* opt_yz;              // [F][R] non-gray board points in the PCA frame (y', z')
+  uint8_t* opt_white;          // [F][R]
+  int* opt_count;              // [F]
+  const uint32_t* rnd_table;   // [kRndTable] PCL RANSAC draws
+  // outputs (device)
+  float* corners;              // [F][ncorners][3]
+  int32_t* status;             // [F]
+  ilcc2_diag* diag;            // [F] (always present internally)
+};
+
+void launch_roi_filter(const Workspace& w, const DevParams& p, cudaStream_t s);
+void launch_cluster(const Workspace& w, const DevParams& p, cudaStream_t s);
+void launch_plane(const Workspace& w, const DevParams& p, cudaStream_t s);
+void launch_pca_gray(const Workspace& w, const DevParams& p, cudaStream_t s);
+void launch_board_fit(const Workspace& w, const DevParams& p, cudaStream_t s);
+cudaError_t configure_kernels();
+size_t cluster_smem_bytes();
+size_t fit_smem_bytes();
+
+}  // namespace ilcc2

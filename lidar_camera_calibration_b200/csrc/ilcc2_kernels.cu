@@ -1,0 +1,1747 @@
+// ilcc2_kernels.cu -- sm_100a kernels of the LiDAR chessboard-corner path.
+//
+// One launch per stage over the whole batch, one CTA per frame in every stage:
+//   K1 roi_filter   setROI                     (ilcc2/src/LidarCornersEst.cpp:48-70)      HBM-bound stream
+//   K2 cluster      EuclideanCluster           (LidarCornersEst.cpp:124-153)              shared-memory hash + union-find
+//   K3 plane        getPlane                   (LidarCornersEst.cpp:190-221)              RANSAC + covariance refit
+//   K4 pca_gray     transformbyPCA + calHist   (LidarCornersEst.cpp:224-372)
+//   K5 board_fit    get_theta_t + getPCDcorners(Optimization.cpp:94-160, Optimization.h:31-107, LidarCornersEst.cpp:374-450, 501-556)
+//
+// Compiled with -fmad=false: every fp32 comparison that decides set membership (ROI box, 0.12 m linkage,
+// 0.03 m plane distance) is an explicit sequence of IEEE operations, so results do not depend on
+// contraction choices; the fp64 sums that feed decisions are reduced in a fixed order (strided
+// per-thread partial sums + xor butterfly).  There is no dense contraction anywhere on this path
+// (largest matrix: 3x3), hence no tensor-core / TMEM use; K1 is the only stage that touches all input bytes.
+#include "ilcc2_internal.h"
+
+#include <float.h>
+#include <math.h>
+
+namespace ilcc2 {
+
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
+  // FLANN L2_Simple<float>: ((dx*dx) + dy*dy) + dz*dz
+  const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  float r = __fmul_rn(dx, dx);
+  r = __fadd_rn(r, __fmul_rn(dy, dy));
+  r = __fadd_rn(r, __fmul_rn(dz, dz));
+  return r;
+}
+
+__device__ __forceinline__ float plane_dist(const float m0, const float m1, const float m2, const float m3,
+                                            float x, float y, float z) {
+  // Eigen SSE Vector4f dot: (a*x + c*z) + (b*y + d)
+  const float t0 = __fadd_rn(__fmul_rn(m0, x), __fmul_rn(m2, z));
+  const float t1 = __fadd_rn(__fmul_rn(m1, y), m3);
+  return fabsf(__fadd_rn(t0, t1));
+}
+
+__device__ __forceinline__ double warp_butterfly(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// Canonical 128-wide reduction for a 128-thread CTA: thread t holds the partial sum of elements k = t (mod 128).
+// total = butterfly over strides 64, 32 (through shared memory), 16..1 (shuffles). Result valid in all threads
+// of warp 0 and broadcast through shared memory to everyone.
+template <int NQ>
+__device__ __forceinline__ void block_reduce128(double (&v)[NQ], double* s_part /* [NQ][128] */, double* s_out /* [NQ] */) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) s_part[q * 128 + t] = v[q];
+  __syncthreads();
+  if (t < 32) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const double* p = s_part + q * 128;
+      double s = (p[t] + p[t + 64]) + (p[t + 32] + p[t + 96]);
+      s = warp_butterfly(s);
+      if (t == 0) s_out[q] = s;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) v[q] = s_out[q];
+  __syncthreads();
+}
+
+// Order-preserving compaction step for one tile of NT elements: returns this thread's output offset within
+// the tile; tile_total = number of selected elements in the tile. All threads of the CTA must call.
+template <int NT>
+__device__ __forceinline__ int block_ordered_offset(bool pred, int* s_warp, int& tile_total) {
+  const unsigned b = __ballot_sync(FULL, pred);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_warp[warp] = __popc(b);
+  __syncthreads();
+  int off = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < NT / 32; ++i) {
+    const int c = s_warp[i];
+    if (i < warp) off += c;
+    tot += c;
+  }
+  __syncthreads();
+  tile_total = tot;
+  return off + __popc(b & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ void roi_limits(const float* click, const DevParams& p, float lim[6]) {
+  // PassThrough::setFilterLimits takes floats; the reference computes click -/+ literal in double
+  lim[0] = (float)((double)click[0] - (double)p.roi_hx);
+  lim[1] = (float)((double)click[0] + (double)p.roi_hx);
+  lim[2] = (float)((double)click[1] - (double)p.roi_hy);
+  lim[3] = (float)((double)click[1] + (double)p.roi_hy);
+  lim[4] = (float)((double)click[2] - (double)p.roi_hz);
+  lim[5] = (float)((double)click[2] + (double)p.roi_hz);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1  roi_filter: the only pass over all input bytes.  One CTA per frame streams the frame's records with
+// 128-bit loads (two tiles in flight per thread), applies the three PassThrough box tests and writes the
+// survivors in input order (ballot + block scan), tracking the click's nearest neighbour on the way.
+// MODE 0: packed 16-byte XYZI; MODE 1: 32-byte records x,y,z@0 intensity@16; MODE 2: generic offsets.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ float4 load_point(const unsigned char* rec, int ox, int oy, int oz, int oi) {
+  if (MODE == 0) {
+    return __ldcs(reinterpret_cast<const float4*>(rec));
+  } else if (MODE == 1) {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(rec));
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(rec + 16));
+    return make_float4(a.x, a.y, a.z, b.x);
+  } else {
+    return make_float4(__ldcs(reinterpret_cast<const float*>(rec + ox)), __ldcs(reinterpret_cast<const float*>(rec + oy)),
+                       __ldcs(reinterpret_cast<const float*>(rec + oz)), __ldcs(reinterpret_cast<const float*>(rec + oi)));
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kRoiThreads) roi_filter_kernel(const Workspace w, const DevParams p) {
+  constexpr int NT = kRoiThreads, U = kRoiUnroll, TILE = NT * U, NW = NT / 32;
+  __shared__ int s_cnt[U * NW];
+  __shared__ int s_off[U * NW];
+  __shared__ int s_tile_total;
+  __shared__ unsigned long long s_key[NW];
+
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  long long start;
+  int n;
+  if (w.frame_off) {
+    start = w.frame_off[f];
+    n = (int)(w.frame_off[f + 1] - start);
+  } else {
+    start = (long long)f * w.pts_per_frame;
+    n = w.pts_per_frame;
+  }
+  const unsigned char* base = w.points + (size_t)start * w.step;
+  const float cx = w.clicks[3 * f + 0], cy = w.clicks[3 * f + 1], cz = w.clicks[3 * f + 2];
+  float lim[6];
+  {
+    const float ck[3] = {cx, cy, cz};
+    roi_limits(ck, p, lim);
+  }
+  float4* out_pts = w.roi_pts + (size_t)f * w.cap;
+  int* out_src = w.roi_src + (size_t)f * w.cap;
+
+  float4 cur[U], nxt[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int idx = u * NT + tid;
+    cur[u] = (idx < n) ? load_point<MODE>(base + (size_t)idx * w.step, w.ox, w.oy, w.oz, w.oi)
+                       : make_float4(NAN, NAN, NAN, 0.f);
+  }
+  int total = 0;
+  unsigned long long best = ~0ull;
+  for (int tile0 = 0; tile0 < n; tile0 += TILE) {
+    // prefetch the next tile before the scan of this one
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = tile0 + TILE + u * NT + tid;
+      nxt[u] = (idx < n) ? load_point<MODE>(base + (size_t)idx * w.step, w.ox, w.oy, w.oz, w.oi)
+                         : make_float4(NAN, NAN, NAN, 0.f);
+    }
+    bool pr[U];
+    int rank[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float4 v = cur[u];
+      bool ok = isfinite(v.x) && isfinite(v.y) && isfinite(v.z);
+      ok = ok && !(v.z < lim[4] || v.z > lim[5]);
+      ok = ok && !(v.x < lim[0] || v.x > lim[1]);
+      ok = ok && !(v.y < lim[2] || v.y > lim[3]);
+      pr[u] = ok;
+      const unsigned b = __ballot_sync(FULL, ok);
+      rank[u] = __popc(b & ((1u << lane) - 1u));
+      if (lane == 0) s_cnt[u * NW + warp] = __popc(b);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // exclusive scan of the U*NW (= 64) counts, u-major = input order
+      static_assert(U * NW == 64, "scan below assumes 64 counts");
+      const int a = s_cnt[lane], b = s_cnt[32 + lane];
+      int sa = a, sb = b;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(FULL, sa, o), tb = __shfl_up_sync(FULL, sb, o);
+        if (lane >= o) {
+          sa += ta;
+          sb += tb;
+        }
+      }
+      const int tot_a = __shfl_sync(FULL, sa, 31);
+      s_off[lane] = sa - a;
+      s_off[32 + lane] = tot_a + sb - b;
+      if (lane == 31) s_tile_total = tot_a + sb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (pr[u]) {
+        const int k = total + s_off[u * NW + warp] + rank[u];
+        const float4 v = cur[u];
+        if (k < w.cap) {
+          out_pts[k] = v;
+          out_src[k] = tile0 + u * NT + tid;
+        }
+        const float d2 = sqdist3(v.x, v.y, v.z, cx, cy, cz);
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)k;
+        best = key < best ? key : best;
+      }
+    }
+    total += s_tile_total;
+#pragma unroll
+    for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+  }
+  // nearest neighbour of the click: min over (dist2, index)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(FULL, best, o);
+    best = other < best ? other : best;
+  }
+  if (lane == 0) s_key[warp] = best;
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 1; i < NW; ++i) best = s_key[i] < best ? s_key[i] : best;
+    const int m = total < w.cap ? total : w.cap;
+    w.roi_count[f] = m;
+    w.nn_key[f] = best;
+    ilcc2_diag* d = w.diag + f;
+    d->n_roi = m;
+    d->nn_index = m == 0 ? 0 : (int)(best & 0xffffffffull);
+    d->status = (m == 0) ? ILCC2_NO_POINTS_IN_ROI : ILCC2_OK;
+  }
+}
+
+void launch_roi_filter(const Workspace& w, const DevParams& p, cudaStream_t s) {
+  if (w.step == 16 && w.ox == 0 && w.oy == 4 && w.oz == 8 && w.oi == 12)
+    roi_filter_kernel<0><<<w.n_frames, kRoiThreads, 0, s>>>(w, p);
+  else if (w.step == 32 && w.ox == 0 && w.oy == 4 && w.oz == 8 && w.oi == 16)
+    roi_filter_kernel<1><<<w.n_frames, kRoiThreads, 0, s>>>(w, p);
+  else
+    roi_filter_kernel<2><<<w.n_frames, kRoiThreads, 0, s>>>(w, p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  cluster: exact single-linkage components at distance < tol (pcl::EuclideanClusterExtraction) of the
+// ROI points of one frame.  Points are hashed into cells of edge 0.95*tol/sqrt(3): two points of one cell
+// are always linked, and linked points are at most 2 cells apart per axis.  Union-find runs over points
+// (parent of a point = head of its cell to begin with); for every occupied cell and each of the 62
+// "forward" offsets of the 5x5x5 stencil, the two cells are joined as soon as one point pair is closer than
+// tol (skipped when they already share a root).  Near offsets (3x3x3) go first so that most far pairs are
+// already connected when they are visited.  Tables live in shared memory up to kClusterSmemPts points, in
+// a per-frame global scratch beyond that.
+// ------------------------------------------------------------------------------------------------
+__constant__ signed char c_fwd_off[62][3];
+
+__device__ __forceinline__ int uf_find(int* par, int x) {
+  volatile int* vp = par;
+  int cur = vp[x];
+  if (cur != x) {
+    int prev = x, nx;
+    while (cur != (nx = vp[cur])) {
+      vp[prev] = nx;
+      prev = cur;
+      cur = nx;
+    }
+  }
+  return cur;
+}
+
+__device__ __forceinline__ void uf_union(int* par, int a, int b) {
+  int ra = uf_find(par, a), rb = uf_find(par, b);
+  while (ra != rb) {
+    if (ra < rb) {
+      const int t = ra;
+      ra = rb;
+      rb = t;
+    }
+    const int old = atomicCAS(&par[ra], ra, rb);  // link the larger root under the smaller
+    if (old == ra) break;
+    ra = uf_find(par, old);
+    rb = uf_find(par, rb);
+  }
+}
+
+__device__ __forceinline__ unsigned hash_cell(int k) {
+  unsigned h = (unsigned)k * 2654435761u;
+  return h ^ (h >> 15);
+}
+
+__global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspace w, const DevParams p) {
+  constexpr int NT = kClusterThreads;
+  extern __shared__ int sm[];
+  __shared__ int s_warp[NT / 32];
+  __shared__ int s_nocc, s_nkept, s_chosen_root;
+
+  const int f = blockIdx.x, tid = threadIdx.x;
+  ilcc2_diag* d = w.diag + f;
+  int* sel = w.sel_idx + (size_t)f * w.cap;
+  const int M = w.roi_count[f];
+  if (M == 0) {
+    if (tid == 0) w.sel_count[f] = 0;
+    return;
+  }
+  int TS;
+  int *key, *head, *nxt, *parent, *occ;
+  if (M <= kClusterSmemPts) {
+    TS = kClusterSmemSlots;
+    key = sm;
+    head = key + TS;
+    nxt = head + TS;
+    parent = nxt + kClusterSmemPts;
+    occ = parent + kClusterSmemPts;
+  } else {
+    TS = w.cl_ts;
+    int* g = w.cl_scratch + (size_t)f * w.cl_stride;
+    key = g;
+    head = key + TS;
+    nxt = head + TS;
+    parent = nxt + w.cap;
+    occ = parent + w.cap;
+  }
+  for (int i = tid; i < TS; i += NT) {
+    key[i] = -1;
+    head[i] = -1;
+  }
+  if (tid == 0) s_nocc = 0;
+  __syncthreads();
+
+  const float4* P = w.roi_pts + (size_t)f * w.cap;
+  float lim[6];
+  roi_limits(w.clicks + 3 * f, p, lim);
+  const int mask = TS - 1;
+  // 1. insert points into the cell hash; per-cell linked lists
+  for (int i = tid; i < M; i += NT) {
+    const float4 q = P[i];
+    int cx = (int)floorf((q.x - lim[0]) / p.cell);
+    int cy = (int)floorf((q.y - lim[2]) / p.cell);
+    int cz = (int)floorf((q.z - lim[4]) / p.cell);
+    cx = min(max(cx, 0), p.ncx - 1);
+    cy = min(max(cy, 0), p.ncy - 1);
+    cz = min(max(cz, 0), p.ncz - 1);
+    const int k = (cz * p.ncy + cy) * p.ncx + cx;
+    unsigned h = hash_cell(k) & mask;
+    for (;;) {
+      const int prev = atomicCAS(&key[h], -1, k);
+      if (prev == -1) {
+        occ[atomicAdd(&s_nocc, 1)] = (int)h;
+        break;
+      }
+      if (prev == k) break;
+      h = (h + 1) & mask;
+    }
+    nxt[i] = atomicExch(&head[h], i);
+    parent[i] = (int)h;  // slot for now
+  }
+  __syncthreads();
+  for (int i = tid; i < M; i += NT) parent[i] = head[parent[i]];  // same cell => same set
+  __syncthreads();
+  // 2. join neighbouring cells
+  const int nocc = s_nocc;
+  const float tol2 = p.tol2;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int o_lo = pass == 0 ? 0 : 13, o_n = pass == 0 ? 13 : 49;
+    const int items = nocc * o_n;
+    for (int it = tid; it < items; it += NT) {
+      const int a = occ[it / o_n];
+      const int o = o_lo + it % o_n;
+      const int ka = key[a];
+      const int ax = ka % p.ncx, ay = (ka / p.ncx) % p.ncy, az = ka / (p.ncx * p.ncy);
+      const int bx = ax + c_fwd_off[o][0], by = ay + c_fwd_off[o][1], bz = az + c_fwd_off[o][2];
+      if (bx < 0 || bx >= p.ncx || by < 0 || by >= p.ncy || bz < 0 || bz >= p.ncz) continue;
+      const int kb = (bz * p.ncy + by) * p.ncx + bx;
+      unsigned h = hash_cell(kb) & mask;
+      int b = -1;
+      for (;;) {
+        const int kk = key[h];
+        if (kk == kb) {
+          b = (int)h;
+          break;
+        }
+        if (kk == -1) break;
+        h = (h + 1) & mask;
+      }
+      if (b < 0) continue;
+      const int ha = head[a], hb = head[b];
+      if (uf_find(parent, ha) == uf_find(parent, hb)) continue;
+      bool linked = false;
+      for (int pa = ha; pa >= 0 && !linked; pa = nxt[pa]) {
+        const float4 qa = __ldg(P + pa);
+        for (int pb = hb; pb >= 0; pb = nxt[pb]) {
+          const float4 qb = __ldg(P + pb);
+          if (sqdist3(qa.x, qa.y, qa.z, qb.x, qb.y, qb.z) < tol2) {
+            uf_union(parent, pa, pb);
+            linked = true;
+            break;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // 3. roots, sizes, lowest index per component (key/head tables are free now)
+  int* root = nxt;
+  int* size_of = key;
+  int* min_idx = head;
+  int* kept = occ;
+  for (int i = tid; i < M; i += NT) {
+    size_of[i] = 0;
+    min_idx[i] = 0x7fffffff;
+  }
+  if (tid == 0) s_nkept = 0;
+  __syncthreads();
+  for (int i = tid; i < M; i += NT) {
+    const int r = uf_find(parent, i);
+    root[i] = r;
+    atomicAdd(&size_of[r], 1);
+    atomicMin(&min_idx[r], i);
+  }
+  __syncthreads();
+  for (int i = tid; i < M; i += NT)
+    if (root[i] == i && size_of[i] >= p.min_cl && size_of[i] <= p.max_cl) kept[atomicAdd(&s_nkept, 1)] = i;
+  __syncthreads();
+  const int nk = s_nkept;
+  if (nk == 0) {
+    if (tid == 0) {
+      d->status = ILCC2_NO_CLUSTER;
+      d->n_clusters = 0;
+      w.sel_count[f] = 0;
+    }
+    return;
+  }
+  // 4. rank kept clusters: size descending, lowest first index first (PCL leaves ties unspecified)
+  int* rank_of = parent;  // indexed by root; parent[] is not needed once root[] is final
+  for (int e = tid; e < nk; e += NT) {
+    const int r = kept[e];
+    const int sz = size_of[r], mi = min_idx[r];
+    int rank = 0;
+    for (int j = 0; j < nk; ++j) {
+      const int r2 = kept[j];
+      const int s2 = size_of[r2];
+      if (s2 > sz || (s2 == sz && min_idx[r2] < mi)) ++rank;
+    }
+    rank_of[r] = rank;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int nn = (int)(w.nn_key[f] & 0xffffffffull);
+    const int rn = root[nn];
+    const bool in = size_of[rn] >= p.min_cl && size_of[rn] <= p.max_cl;
+    int rank = in ? rank_of[rn] : 0;
+    const int delta = w.pdelta ? (int)w.pdelta[f] : 0;
+    if (delta > 0) rank = min(rank + delta, nk - 1);
+    if (delta < 0) rank = max(rank + delta, 0);
+    int chosen = kept[0];
+    for (int j = 0; j < nk; ++j)
+      if (rank_of[kept[j]] == rank) chosen = kept[j];
+    s_chosen_root = chosen;
+    d->n_clusters = nk;
+    d->click_in_cluster = in ? 1 : 0;
+    d->cluster_rank = rank;
+    d->n_cluster_pts = size_of[chosen];
+  }
+  __syncthreads();
+  // 5. chosen cluster in input order
+  const int chosen = s_chosen_root;
+  int total = 0;
+  for (int base = 0; base < M; base += NT) {
+    const int i = base + tid;
+    const bool pr = i < M && root[i] == chosen;
+    int tile_total;
+    const int off = block_ordered_offset<NT>(pr, s_warp, tile_total);
+    if (pr) sel[total + off] = i;
+    total += tile_total;
+  }
+  if (tid == 0) w.sel_count[f] = total;
+}
+
+size_t cluster_smem_bytes() { return sizeof(int) * (2 * kClusterSmemSlots + 3 * kClusterSmemPts); }
+
+void launch_cluster(const Workspace& w, const DevParams& p, cudaStream_t s) {
+  cluster_kernel<<<w.n_frames, kClusterThreads, cluster_smem_bytes(), s>>>(w, p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// symmetric 3x3 eigen solvers (device restatements; see DESIGN.md for what each one mirrors)
+// ------------------------------------------------------------------------------------------------
+// double cyclic Jacobi, fixed 12 sweeps: used for the least-squares plane refit.
+__device__ void jacobi3d(const double A[6], double ev[3], double V[3][3]) {
+  double a[3][3] = {{A[0], A[1], A[2]}, {A[1], A[3], A[4]}, {A[2], A[4], A[5]}};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    for (int pi = 0; pi < 2; ++pi)
+      for (int q = pi + 1; q < 3; ++q) {
+        const double apq = a[pi][q];
+        if (apq == 0.0) continue;
+        const double theta = (a[q][q] - a[pi][pi]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0);
+        const double s = t * c;
+        for (int k = 0; k < 3; ++k) {
+          const double akp = a[k][pi], akq = a[k][q];
+          a[k][pi] = c * akp - s * akq;
+          a[k][q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double apk = a[pi][k], aqk = a[q][k];
+          a[pi][k] = c * apk - s * aqk;
+          a[q][k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = V[k][pi], vkq = V[k][q];
+          V[k][pi] = c * vkp - s * vkq;
+          V[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  ev[0] = a[0][0];
+  ev[1] = a[1][1];
+  ev[2] = a[2][2];
+}
+
+__device__ __forceinline__ float eig_hypotf(float x, float y) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  float pp, qp;
+  if (ax > ay) {
+    pp = ax;
+    qp = ay / pp;
+  } else {
+    pp = ay;
+    qp = ax / pp;
+  }
+  if (pp == 0.0f) return 0.0f;
+  return pp * sqrtf(1.0f + qp * qp);
+}
+
+// float, Eigen-3.2-style SelfAdjointEigenSolver<Matrix3f>::compute (tridiagonalise, implicit QR with
+// Wilkinson shift, deflation at 1e-5, ascending sort): defines the SIGN of the PCA axes
+// (LidarCornersEst.cpp:337-343).  cov row-major; Q[r][c] columns = eigenvectors.
+__device__ void eigen3f(const float cov[9], float evals[3], float Q[3][3]) {
+  float m00 = cov[0], m10 = cov[3], m11 = cov[4], m20 = cov[6], m21 = cov[7], m22 = cov[8];
+  float scale = fabsf(m00);
+  scale = fmaxf(scale, fabsf(m10));
+  scale = fmaxf(scale, fabsf(m11));
+  scale = fmaxf(scale, fabsf(m20));
+  scale = fmaxf(scale, fabsf(m21));
+  scale = fmaxf(scale, fabsf(m22));
+  if (scale == 0.0f) scale = 1.0f;
+  m00 /= scale; m10 /= scale; m11 /= scale; m20 /= scale; m21 /= scale; m22 /= scale;
+  float diag[3], sub[2];
+  diag[0] = m00;
+  const float v1norm2 = m20 * m20;
+  if (v1norm2 <= FLT_MIN) {
+    diag[1] = m11;
+    diag[2] = m22;
+    sub[0] = m10;
+    sub[1] = m21;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) Q[r][c] = (r == c) ? 1.0f : 0.0f;
+  } else {
+    const float beta = sqrtf(m10 * m10 + v1norm2);
+    const float inv_beta = 1.0f / beta;
+    const float m01 = m10 * inv_beta;
+    const float m02 = m20 * inv_beta;
+    const float q = 2.0f * m01 * m21 + m02 * (m22 - m11);
+    diag[1] = m11 + m02 * q;
+    diag[2] = m22 - m02 * q;
+    sub[0] = beta;
+    sub[1] = m21 - m01 * q;
+    Q[0][0] = 1; Q[0][1] = 0;   Q[0][2] = 0;
+    Q[1][0] = 0; Q[1][1] = m01; Q[1][2] = m02;
+    Q[2][0] = 0; Q[2][1] = m02; Q[2][2] = -m01;
+  }
+  int end = 2, start = 0, iter = 0;
+  const float precision = 1e-5f;
+  while (end > 0) {
+    for (int i = start; i < end; ++i)
+      if (fabsf(sub[i]) <= (fabsf(diag[i]) + fabsf(diag[i + 1])) * precision) sub[i] = 0.0f;
+    while (end > 0 && sub[end - 1] == 0.0f) end--;
+    if (end <= 0) break;
+    iter++;
+    if (iter > 90) break;
+    start = end - 1;
+    while (start > 0 && sub[start - 1] != 0.0f) start--;
+    const float td = (diag[end - 1] - diag[end]) * 0.5f;
+    const float e = sub[end - 1];
+    float mu = diag[end];
+    if (td == 0.0f) {
+      mu -= fabsf(e);
+    } else if (e != 0.0f) {
+      const float e2 = e * e;
+      const float h = eig_hypotf(td, e);
+      if (e2 == 0.0f)
+        mu -= e / ((td + (td > 0.0f ? h : -h)) / e);
+      else
+        mu -= e2 / (td + (td > 0.0f ? h : -h));
+    }
+    float x = diag[start] - mu;
+    float z = sub[start];
+    for (int k = start; k < end; ++k) {
+      float c, s;
+      if (z == 0.0f) {
+        c = x < 0.0f ? -1.0f : 1.0f;
+        s = 0.0f;
+      } else if (x == 0.0f) {
+        c = 0.0f;
+        s = z < 0.0f ? 1.0f : -1.0f;
+      } else if (fabsf(x) > fabsf(z)) {
+        const float t = z / x;
+        float u = sqrtf(1.0f + t * t);
+        if (x < 0.0f) u = -u;
+        c = 1.0f / u;
+        s = -t * c;
+      } else {
+        const float t = x / z;
+        float u = sqrtf(1.0f + t * t);
+        if (z < 0.0f) u = -u;
+        s = -1.0f / u;
+        c = -t * s;
+      }
+      const float sdk = s * diag[k] + c * sub[k];
+      const float dkp1 = s * sub[k] + c * diag[k + 1];
+      diag[k] = c * (c * diag[k] - s * sub[k]) - s * (c * sub[k] - s * diag[k + 1]);
+      diag[k + 1] = s * sdk + c * dkp1;
+      sub[k] = c * sdk - s * dkp1;
+      if (k > start) sub[k - 1] = c * sub[k - 1] - s * z;
+      x = sub[k];
+      if (k < end - 1) {
+        z = -s * sub[k + 1];
+        sub[k + 1] = c * sub[k + 1];
+      }
+      for (int r = 0; r < 3; ++r) {
+        const float xi = Q[r][k], yi = Q[r][k + 1];
+        Q[r][k] = c * xi - s * yi;
+        Q[r][k + 1] = s * xi + c * yi;
+      }
+    }
+  }
+  for (int i = 0; i < 2; ++i) {
+    int k = 0;
+    for (int j = 1; j < 3 - i; ++j)
+      if (diag[i + j] < diag[i + k]) k = j;
+    if (k > 0) {
+      const float t = diag[i];
+      diag[i] = diag[i + k];
+      diag[i + k] = t;
+      for (int r = 0; r < 3; ++r) {
+        const float q = Q[r][i];
+        Q[r][i] = Q[r][i + k];
+        Q[r][i + k] = q;
+      }
+    }
+  }
+  for (int i = 0; i < 3; ++i) evals[i] = diag[i] * scale;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3  plane: pcl::SACSegmentation(PLANE, RANSAC, 0.03, optimizeCoefficients) on the chosen cluster.
+// Thread 0 walks PCL's sample sequence (shuffled-index swaps driven by the fixed-seed draw table), every
+// hypothesis is scored by the whole CTA; then the LS refit (fp64 covariance, 128-wide canonical sums,
+// smallest eigenvector) and the final inlier re-selection, written in input order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool sample_good(const float4 p0, const float4 p1, const float4 p2) {
+  const float r0 = (p1.x - p0.x) / (p2.x - p0.x);
+  const float r1 = (p1.y - p0.y) / (p2.y - p0.y);
+  const float r2 = (p1.z - p0.z) / (p2.z - p0.z);
+  return (r0 != r1) || (r2 != r1);
+}
+
+__device__ __forceinline__ bool plane_from_3(const float4 p0, const float4 p1, const float4 p2, float m[4]) {
+  const float a0 = p1.x - p0.x, a1 = p1.y - p0.y, a2 = p1.z - p0.z;
+  const float b0 = p2.x - p0.x, b1 = p2.y - p0.y, b2 = p2.z - p0.z;
+  const float r0 = a0 / b0, r1 = a1 / b1, r2 = a2 / b2;
+  if (r0 == r1 && r2 == r1) return false;
+  float n0 = a1 * b2 - a2 * b1;
+  float n1 = a2 * b0 - a0 * b2;
+  float n2 = a0 * b1 - a1 * b0;
+  float nn = n0 * n0;
+  nn = nn + n1 * n1;
+  nn = nn + n2 * n2;
+  const float norm = sqrtf(nn);
+  n0 = n0 / norm;
+  n1 = n1 / norm;
+  n2 = n2 / norm;
+  float dd = n0 * p0.x;
+  dd = dd + n1 * p0.y;
+  dd = dd + n2 * p0.z;
+  m[0] = n0;
+  m[1] = n1;
+  m[2] = n2;
+  m[3] = -1.0f * dd;
+  return true;
+}
+
+__global__ void __launch_bounds__(kPlaneThreads) plane_kernel(const Workspace w, const DevParams p) {
+  constexpr int NT = kPlaneThreads;
+  __shared__ float s_model[4];
+  __shared__ int s_ctrl;  // 1: score s_model, 0: stop
+  __shared__ int s_have;  // after the loop: a model was found (separate word: s_ctrl may still be being read)
+  __shared__ int s_warp[NT / 32];
+  __shared__ int s_cnt[NT / 32];
+  __shared__ double s_part[9 * 128];
+  __shared__ double s_out[9];
+
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  ilcc2_diag* d = w.diag + f;
+  if (d->status != ILCC2_OK) {
+    if (tid == 0) w.brd_count[f] = 0;
+    return;
+  }
+  const int C = w.sel_count[f];
+  const int* S = w.sel_idx + (size_t)f * w.cap;
+  const float4* P = w.roi_pts + (size_t)f * w.cap;
+  int* perm = w.tmp_idx + (size_t)f * w.cap;
+  int* brd = w.brd_idx + (size_t)f * w.cap;
+  const double thr = p.ransac_thr;
+
+  for (int i = tid; i < C; i += NT) perm[i] = i;
+  __syncthreads();
+
+  // RANSAC control state lives in thread 0's registers
+  int iterations = 0, skipped = 0, n_best = -0x7fffffff, draw = 0;
+  bool have_model = false;
+  double k = 1.0;
+  float best[4] = {0.f, 0.f, 0.f, 0.f};
+  const int max_skip = p.ransac_max_iter * 10;
+  for (;;) {
+    if (tid == 0) {
+      int ctrl = 0;
+      if (C >= 3) {
+        while ((double)iterations < k && skipped < max_skip) {
+          bool good = false;
+          float4 q0, q1, q2;
+          for (int chk = 0; chk < 1000 && !good; ++chk) {
+            if (draw + 3 > kRndTable) break;
+            for (int i = 0; i < 3; ++i) {
+              const int j = i + (int)(w.rnd_table[draw++] % (unsigned)(C - i));
+              const int t = perm[i];
+              perm[i] = perm[j];
+              perm[j] = t;
+            }
+            q0 = P[S[perm[0]]];
+            q1 = P[S[perm[1]]];
+            q2 = P[S[perm[2]]];
+            good = sample_good(q0, q1, q2);
+          }
+          if (!good) break;
+          float m[4];
+          if (!plane_from_3(q0, q1, q2, m)) {
+            ++skipped;
+            continue;
+          }
+          s_model[0] = m[0];
+          s_model[1] = m[1];
+          s_model[2] = m[2];
+          s_model[3] = m[3];
+          ctrl = 1;
+          break;
+        }
+      }
+      s_ctrl = ctrl;
+    }
+    __syncthreads();
+    if (s_ctrl == 0) break;
+    const float m0 = s_model[0], m1 = s_model[1], m2 = s_model[2], m3 = s_model[3];
+    int cnt = 0;
+    for (int i = tid; i < C; i += NT) {
+      const float4 q = __ldg(P + S[i]);
+      cnt += ((double)plane_dist(m0, m1, m2, m3, q.x, q.y, q.z) < thr) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+      int total = 0;
+      for (int i = 0; i < NT / 32; ++i) total += s_cnt[i];
+      if (total > n_best) {
+        n_best = total;
+        best[0] = m0;
+        best[1] = m1;
+        best[2] = m2;
+        best[3] = m3;
+        have_model = true;
+        const double wr = (double)n_best * (1.0 / (double)C);
+        double p_no = 1.0 - pow(wr, 3.0);
+        p_no = fmax(p_no, DBL_EPSILON);
+        p_no = fmin(p_no, 1.0 - DBL_EPSILON);
+        k = p.ransac_log_prob / log(p_no);
+      }
+      ++iterations;
+      if (iterations > p.ransac_max_iter) k = -1.0;  // PCL breaks out of the loop here
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    s_have = have_model ? 1 : 0;
+    s_model[0] = best[0];
+    s_model[1] = best[1];
+    s_model[2] = best[2];
+    s_model[3] = best[3];
+    d->ransac_iterations = iterations;
+  }
+  __syncthreads();
+  if (s_have == 0) {
+    if (tid == 0) {
+      d->status = ILCC2_RANSAC_FAILED;
+      w.brd_count[f] = 0;
+    }
+    return;
+  }
+  // inliers of the best sample model, input order (ROI indices), into perm[] (no longer needed)
+  float m0 = s_model[0], m1 = s_model[1], m2 = s_model[2], m3 = s_model[3];
+  int* inl = perm;
+  __syncthreads();
+  int ni = 0;
+  for (int base = 0; base < C; base += NT) {
+    const int i = base + tid;
+    int ri = 0;
+    bool pr = false;
+    if (i < C) {
+      ri = S[i];
+      const float4 q = __ldg(P + ri);
+      pr = (double)plane_dist(m0, m1, m2, m3, q.x, q.y, q.z) < thr;
+    }
+    int tile_total;
+    const int off = block_ordered_offset<NT>(pr, s_warp, tile_total);
+    if (pr) inl[ni + off] = ri;
+    ni += tile_total;
+  }
+  __syncthreads();
+  int nb;
+  if (ni >= 4) {
+    // LS refit: moments about the first inlier, fp64, canonical 128-wide order
+    const float4 ref = P[inl[0]];
+    double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int kk = tid; kk < ni; kk += NT) {
+      const float4 q = __ldg(P + inl[kk]);
+      const double dx = (double)q.x - (double)ref.x;
+      const double dy = (double)q.y - (double)ref.y;
+      const double dz = (double)q.z - (double)ref.z;
+      v[0] += dx;
+      v[1] += dy;
+      v[2] += dz;
+      v[3] += dx * dx;
+      v[4] += dx * dy;
+      v[5] += dx * dz;
+      v[6] += dy * dy;
+      v[7] += dy * dz;
+      v[8] += dz * dz;
+    }
+    block_reduce128<9>(v, s_part, s_out);
+    if (tid == 0) {
+      const double inv_n = 1.0 / (double)ni;
+      const double mx = v[0] * inv_n, my = v[1] * inv_n, mz = v[2] * inv_n;
+      double A[6];
+      A[0] = v[3] * inv_n - mx * mx;
+      A[1] = v[4] * inv_n - mx * my;
+      A[2] = v[5] * inv_n - mx * mz;
+      A[3] = v[6] * inv_n - my * my;
+      A[4] = v[7] * inv_n - my * mz;
+      A[5] = v[8] * inv_n - mz * mz;
+      double ev[3], V[3][3];
+      jacobi3d(A, ev, V);
+      int c0 = 0;
+      if (ev[1] < ev[c0]) c0 = 1;
+      if (ev[2] < ev[c0]) c0 = 2;
+      double nx = V[0][c0], ny = V[1][c0], nz = V[2][c0];
+      const double nn = sqrt(nx * nx + ny * ny + nz * nz);
+      nx /= nn;
+      ny /= nn;
+      nz /= nn;
+      const double cx = (double)ref.x + mx, cy = (double)ref.y + my, cz = (double)ref.z + mz;
+      s_model[0] = (float)nx;
+      s_model[1] = (float)ny;
+      s_model[2] = (float)nz;
+      s_model[3] = (float)(-(nx * cx + ny * cy + nz * cz));
+    }
+    __syncthreads();
+    m0 = s_model[0];
+    m1 = s_model[1];
+    m2 = s_model[2];
+    m3 = s_model[3];
+    nb = 0;
+    for (int base = 0; base < C; base += NT) {
+      const int i = base + tid;
+      int ri = 0;
+      bool pr = false;
+      if (i < C) {
+        ri = S[i];
+        const float4 q = __ldg(P + ri);
+        pr = (double)plane_dist(m0, m1, m2, m3, q.x, q.y, q.z) < thr;
+      }
+      int tile_total;
+      const int off = block_ordered_offset<NT>(pr, s_warp, tile_total);
+      if (pr) brd[nb + off] = ri;
+      nb += tile_total;
+    }
+  } else {
+    for (int i = tid; i < ni; i += NT) brd[i] = inl[i];
+    nb = ni;
+  }
+  if (tid == 0) {
+    d->n_ransac_inliers = ni;
+    d->n_board = nb;
+    d->plane[0] = m0;
+    d->plane[1] = m1;
+    d->plane[2] = m2;
+    d->plane[3] = m3;
+    w.brd_count[f] = nb;
+    if (nb < 3 || nb < p.min_board) d->status = (ni == 0 && nb == 0) ? ILCC2_RANSAC_FAILED : ILCC2_PLANE_TOO_SMALL;
+  }
+}
+
+void launch_plane(const Workspace& w, const DevParams& p, cudaStream_t s) {
+  plane_kernel<<<w.n_frames, kPlaneThreads, 0, s>>>(w, p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4  pca_gray: transformbyPCA (centroid, covariance/N, eigenvectors, T = [V^T | -V^T c]) + calHist /
+// get_gray_zone + the black/white classification of get_theta_t; emits the optimiser's point list.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void xform_pt(const float* T, float x, float y, float z, float out[3]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float v = __fmul_rn(T[4 * r + 0], x);
+    v = __fadd_rn(v, __fmul_rn(T[4 * r + 1], y));
+    v = __fadd_rn(v, __fmul_rn(T[4 * r + 2], z));
+    out[r] = __fadd_rn(v, T[4 * r + 3]);
+  }
+}
+
+__global__ void __launch_bounds__(kPlaneThreads) pca_gray_kernel(const Workspace w, const DevParams p) {
+  constexpr int NT = kPlaneThreads;
+  __shared__ double s_part[6 * 128];
+  __shared__ double s_out[6];
+  __shared__ float s_T[16];
+  __shared__ float s_c[3];
+  __shared__ int s_hist[4097];
+  __shared__ float s_mm[2 * (NT / 32)];
+  __shared__ double s_gray[2];
+  __shared__ int s_status;
+  __shared__ int s_warp[NT / 32];
+
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  ilcc2_diag* d = w.diag + f;
+  if (d->status != ILCC2_OK) {
+    if (tid == 0) w.opt_count[f] = 0;
+    return;
+  }
+  const int B = w.brd_count[f];
+  const int* BI = w.brd_idx + (size_t)f * w.cap;
+  const float4* P = w.roi_pts + (size_t)f * w.cap;
+  const int NB = p.hist_bins;
+
+  // centroid + intensity statistics
+  double v[4] = {0, 0, 0, 0};
+  float imin = FLT_MAX, imax = -FLT_MAX;
+  for (int k = tid; k < B; k += NT) {
+    const float4 q = __ldg(P + BI[k]);
+    v[0] += (double)q.x;
+    v[1] += (double)q.y;
+    v[2] += (double)q.z;
+    v[3] += (double)q.w;
+    imin = fminf(imin, q.w);
+    imax = fmaxf(imax, q.w);
+  }
+  block_reduce128<4>(v, s_part, s_out);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    imin = fminf(imin, __shfl_xor_sync(FULL, imin, o));
+    imax = fmaxf(imax, __shfl_xor_sync(FULL, imax, o));
+  }
+  if (lane == 0) {
+    s_mm[warp] = imin;
+    s_mm[NT / 32 + warp] = imax;
+  }
+  if (tid == 0) {
+    s_c[0] = (float)(v[0] / (double)B);
+    s_c[1] = (float)(v[1] / (double)B);
+    s_c[2] = (float)(v[2] / (double)B);
+  }
+  for (int i = tid; i <= NB; i += NT) s_hist[i] = 0;
+  __syncthreads();
+  const double isum = v[3];
+  for (int i = 0; i < NT / 32; ++i) {
+    imin = fminf(imin, s_mm[i]);
+    imax = fmaxf(imax, s_mm[NT / 32 + i]);
+  }
+  const float c0 = s_c[0], c1 = s_c[1], c2 = s_c[2];
+  const double mn = (double)imin, mx = (double)imax;
+  const double mean = isum / (double)B;
+  const double factor = (double)NB / (mx - mn);
+  // covariance (centred with the float centroid, products in double) + histogram
+  double m[6] = {0, 0, 0, 0, 0, 0};
+  for (int k = tid; k < B; k += NT) {
+    const float4 q = __ldg(P + BI[k]);
+    const double dx = (double)__fsub_rn(q.x, c0);
+    const double dy = (double)__fsub_rn(q.y, c1);
+    const double dz = (double)__fsub_rn(q.z, c2);
+    m[0] += dx * dx;
+    m[1] += dx * dy;
+    m[2] += dx * dz;
+    m[3] += dy * dy;
+    m[4] += dy * dz;
+    m[5] += dz * dz;
+    if (mx > mn) {
+      int bin = (int)round(((double)q.w - mn) * factor);
+      bin = min(max(bin, 0), NB);
+      atomicAdd(&s_hist[bin], 1);
+    }
+  }
+  block_reduce128<6>(m, s_part, s_out);
+  if (tid == 0) {
+    float cov[9];
+    const float cxx = (float)(m[0] / (double)B), cxy = (float)(m[1] / (double)B), cxz = (float)(m[2] / (double)B);
+    const float cyy = (float)(m[3] / (double)B), cyz = (float)(m[4] / (double)B), czz = (float)(m[5] / (double)B);
+    cov[0] = cxx; cov[1] = cxy; cov[2] = cxz;
+    cov[3] = cxy; cov[4] = cyy; cov[5] = cyz;
+    cov[6] = cxz; cov[7] = cyz; cov[8] = czz;
+    float ev[3], Q[3][3];
+    eigen3f(cov, ev, Q);
+    float v0[3] = {Q[0][0], Q[1][0], Q[2][0]}, v1[3] = {Q[0][1], Q[1][1], Q[2][1]}, v2[3];
+    v2[0] = v0[1] * v1[2] - v0[2] * v1[1];
+    v2[1] = v0[2] * v1[0] - v0[0] * v1[2];
+    v2[2] = v0[0] * v1[1] - v0[1] * v1[0];
+    const float* rows[3] = {v0, v1, v2};
+    for (int r = 0; r < 3; ++r) {
+      s_T[4 * r + 0] = rows[r][0];
+      s_T[4 * r + 1] = rows[r][1];
+      s_T[4 * r + 2] = rows[r][2];
+      float t = rows[r][0] * c0;
+      t = t + rows[r][1] * c1;
+      t = t + rows[r][2] * c2;
+      s_T[4 * r + 3] = -1.0f * t;
+    }
+    s_T[12] = 0.f; s_T[13] = 0.f; s_T[14] = 0.f; s_T[15] = 1.f;
+    for (int i = 0; i < 16; ++i) d->pca[i] = s_T[i];
+    for (int i = 0; i < 3; ++i) d->eigvals[i] = ev[i];
+    // calHist mode rule
+    int st = ILCC2_OK;
+    double low = -1.0, high = -1.0;
+    d->hist_min = mn;
+    d->hist_max = mx;
+    d->hist_mean = mean;
+    if (!(mx > mn) || NB <= 0) {
+      st = ILCC2_DEGENERATE_INTENSITY;
+    } else {
+      const double bin_width = (mx - mn) / (double)NB;
+      bool low_found = false, high_found = false;
+      int prev_count = 0x7fffffff;
+      for (;;) {
+        int bestc = -1, best_bin = -1;
+        for (int b = 0; b < NB; ++b) {
+          const int h = s_hist[b];
+          if (h < prev_count && h > bestc) {
+            bestc = h;
+            best_bin = b;
+          }
+        }
+        if (bestc < 0) break;
+        prev_count = bestc;
+        const double edge = bin_width * (double)best_bin + mn;
+        if (edge > mean && !high_found) {
+          high_found = true;
+          high = edge;
+        }
+        if (edge < mean && !low_found) {
+          low_found = true;
+          low = edge;
+        }
+        if (low_found && high_found) break;
+      }
+      if (!low_found || !high_found) st = ILCC2_DEGENERATE_INTENSITY;
+    }
+    d->r_low = low;
+    d->r_high = high;
+    const double rate = p.gray_rate;
+    double g0 = 0.0, g1 = 0.0;
+    if (st == ILCC2_OK) {
+      g0 = ((rate - 1.0) * low + high) / rate;
+      g1 = (low + (rate - 1.0) * high) / rate;
+    }
+    d->gray[0] = g0;
+    d->gray[1] = g1;
+    s_gray[0] = g0;
+    s_gray[1] = g1;
+    s_status = st;
+    if (st != ILCC2_OK) d->status = st;
+  }
+  __syncthreads();
+  if (s_status != ILCC2_OK) {
+    if (tid == 0) w.opt_count[f] = 0;
+    return;
+  }
+  // classify (Optimization.cpp:114-125) and emit (y', z', white) in board order
+  const double g0 = s_gray[0], g1 = s_gray[1];
+  float2* oyz = w.opt_yz + (size_t)f * w.cap;
+  uint8_t* owh = w.opt_white + (size_t)f * w.cap;
+  int ns = 0;
+  for (int base = 0; base < B; base += NT) {
+    const int k = base + tid;
+    bool pr = false;
+    int white = 0;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < B) {
+      q = __ldg(P + BI[k]);
+      const double I = (double)q.w;
+      if (I < g0) {
+        pr = true;
+        white = 0;
+      } else if (I > g1) {
+        pr = true;
+        white = 1;
+      }
+    }
+    int tile_total;
+    const int off = block_ordered_offset<NT>(pr, s_warp, tile_total);
+    if (pr) {
+      float t[3];
+      xform_pt(s_T, q.x, q.y, q.z, t);
+      oyz[ns + off] = make_float2(t[1], t[2]);
+      owh[ns + off] = (uint8_t)white;
+    }
+    ns += tile_total;
+  }
+  if (tid == 0) {
+    w.opt_count[f] = ns;
+    d->n_opt = ns;
+    if (ns == 0) d->status = ILCC2_NO_OPT_POINTS;
+  }
+}
+
+void launch_pca_gray(const Workspace& w, const DevParams& p, cudaStream_t s) {
+  pca_gray_kernel<<<w.n_frames, kPlaneThreads, 0, s>>>(w, p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5  board_fit: the virtual-chessboard pose optimisation (one ceres::Solve per phase in the reference).
+// One warp per (frame, colour hypothesis).  Every lane owns the points k = lane (mod 32); residuals and
+// the 3-column Jacobian are evaluated in fp64, cost / J^T r / J^T J are reduced by a 32-lane xor butterfly,
+// and the 3x3 trust-region dogleg step (subspace dogleg, as configured at Optimization.cpp:145-149) is
+// computed redundantly by all lanes, so a solve needs no shared-memory traffic and no block barrier.
+// ------------------------------------------------------------------------------------------------
+struct VbModel {
+  int W, H, tlw, oob;
+  double inv_g, wg2, hg2, ha, hb;
+};
+
+__device__ __forceinline__ double vb_point(const VbModel& M, double y, double z, int white, double c, double s,
+                                           double ty, double tz, double& si, double& sj) {
+  const double yy = (y * c - z * s) + ty;
+  const double zz = (z * c + y * s) + tz;
+  const double fi = (yy + M.wg2) * M.inv_g;
+  const double fj = (zz + M.hg2) * M.inv_g;
+  si = 0.0;
+  sj = 0.0;
+  if (fi > 0.0 && fi < (double)M.W && fj > 0.0 && fj < (double)M.H) {
+    const double ifl = floor(fi), jfl = floor(fj);
+    const int same = ((((int)ifl) ^ ((int)jfl)) & 1) == 0;
+    const int cell_white = same ? M.tlw : !M.tlw;
+    if (white == cell_white) return 0.0;
+    double ei, ej;
+    const double di = fi - ifl, dj = fj - jfl;
+    if (di > 0.5) {
+      ei = ceil(fi) - fi;
+      si = -1.0;
+    } else {
+      ei = di;
+      si = 1.0;
+    }
+    if (dj > 0.5) {
+      ej = ceil(fj) - fj;
+      sj = -1.0;
+    } else {
+      ej = dj;
+      sj = 1.0;
+    }
+    return ei + ej;
+  }
+  if (M.oob) {
+    double ei, ej;
+    const double a0 = fabs(fi), a1 = fabs(fi - (double)M.W);
+    if (a0 < a1) {
+      ei = a0;
+      si = fi < 0.0 ? -1.0 : 1.0;
+    } else {
+      ei = a1;
+      si = (fi - (double)M.W) < 0.0 ? -1.0 : 1.0;
+    }
+    const double b0 = fabs(fj), b1 = fabs(fj - (double)M.H);
+    if (b0 < b1) {
+      ej = b0;
+      sj = fj < 0.0 ? -1.0 : 1.0;
+    } else {
+      ej = b1;
+      sj = (fj - (double)M.H) < 0.0 ? -1.0 : 1.0;
+    }
+    return ei + ej;
+  }
+  return 0.0;
+}
+
+__device__ __forceinline__ double huber_cost(const VbModel& M, double r) {
+  const double s = r * r;
+  if (s > M.hb) return 0.5 * (2.0 * M.ha * r - M.hb);
+  return 0.5 * s;
+}
+
+struct FitPoints {
+  const float2* yz;
+  const uint8_t* white;
+  int n;
+};
+
+__device__ double eval_cost(const FitPoints& F, const VbModel& M, const double x[3], int lane) {
+  double s, c;
+  sincos(x[0], &s, &c);
+  double acc = 0.0;
+  for (int k = lane; k < F.n; k += 32) {
+    const float2 q = F.yz[k];
+    double si, sj;
+    const double r = vb_point(M, (double)q.x, (double)q.y, F.white[k], c, s, x[1], x[2], si, sj);
+    if (r != 0.0) acc += huber_cost(M, r);
+  }
+  return warp_butterfly(acc);
+}
+
+__device__ void eval_jac(const FitPoints& F, const VbModel& M, const double x[3], int lane, double& cost,
+                         double g[3], double H[6]) {
+  double s, c;
+  sincos(x[0], &s, &c);
+  double a[10];
+#pragma unroll
+  for (int q = 0; q < 10; ++q) a[q] = 0.0;
+  for (int k = lane; k < F.n; k += 32) {
+    const float2 qq = F.yz[k];
+    const double y = (double)qq.x, z = (double)qq.y;
+    double si, sj;
+    const double r = vb_point(M, y, z, F.white[k], c, s, x[1], x[2], si, sj);
+    if (r == 0.0) continue;
+    const double dyy = -(y * s) - (z * c);
+    const double dzz = (y * c) - (z * s);
+    double j0 = (si * dyy) * M.inv_g + (sj * dzz) * M.inv_g;
+    double j1 = si * M.inv_g;
+    double j2 = sj * M.inv_g;
+    double rr = r;
+    const double sq = r * r;
+    if (sq > M.hb) {
+      const double rho1 = M.ha / r;
+      const double sc = sqrt(rho1);
+      j0 *= sc;
+      j1 *= sc;
+      j2 *= sc;
+      rr = sc * r;
+    }
+    a[0] += huber_cost(M, r);
+    a[1] += j0 * rr;
+    a[2] += j1 * rr;
+    a[3] += j2 * rr;
+    a[4] += j0 * j0;
+    a[5] += j0 * j1;
+    a[6] += j0 * j2;
+    a[7] += j1 * j1;
+    a[8] += j1 * j2;
+    a[9] += j2 * j2;
+  }
+#pragma unroll
+  for (int q = 0; q < 10; ++q) a[q] = warp_butterfly(a[q]);
+  cost = a[0];
+  g[0] = a[1];
+  g[1] = a[2];
+  g[2] = a[3];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) H[q] = a[4 + q];
+}
+
+// --- 3x3 trust-region machinery (all lanes execute it redundantly on identical inputs) ---
+struct Dogleg {
+  double radius, mu;
+  int reuse;
+  double diag[3], grad[3], gn[3], alpha;
+  int sub1d;
+  double U[3][2], sub_g[2], sub_B[3];
+  double step_norm;
+};
+
+__device__ __forceinline__ double norm3(const double v[3]) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+
+__device__ __forceinline__ double quad3(const double H[6], const double u[3], const double v[3]) {
+  const double h0 = H[0] * v[0] + H[1] * v[1] + H[2] * v[2];
+  const double h1 = H[1] * v[0] + H[3] * v[1] + H[4] * v[2];
+  const double h2 = H[2] * v[0] + H[4] * v[1] + H[5] * v[2];
+  return u[0] * h0 + u[1] * h1 + u[2] * h2;
+}
+
+__device__ bool chol3_solve(const double A[6], const double b[3], double x[3]) {
+  if (!(A[0] > 0.0)) return false;
+  const double l00 = sqrt(A[0]);
+  const double l10 = A[1] / l00;
+  const double l20 = A[2] / l00;
+  double t = A[3] - l10 * l10;
+  if (!(t > 0.0)) return false;
+  const double l11 = sqrt(t);
+  const double l21 = (A[4] - l20 * l10) / l11;
+  t = A[5] - l20 * l20 - l21 * l21;
+  if (!(t > 0.0)) return false;
+  const double l22 = sqrt(t);
+  const double y0 = b[0] / l00;
+  const double y1 = (b[1] - l10 * y0) / l11;
+  const double y2 = (b[2] - l20 * y0 - l21 * y1) / l22;
+  x[2] = y2 / l22;
+  x[1] = (y1 - l21 * x[2]) / l11;
+  x[0] = (y0 - l10 * x[1] - l20 * x[2]) / l00;
+  return isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]);
+}
+
+__device__ bool tr2_eval(double a, double b, double dd, double g0, double g1, double y, double x[2], double& n2,
+                         double& q) {
+  const double ay = a + y, dy = dd + y;
+  const double det = ay * dy - b * b;
+  if (!(ay > 0.0) || !(det > 0.0)) return false;
+  x[0] = -(dy * g0 - b * g1) / det;
+  x[1] = -(ay * g1 - b * g0) / det;
+  n2 = x[0] * x[0] + x[1] * x[1];
+  const double w0 = (dy * x[0] - b * x[1]) / det;
+  const double w1 = (ay * x[1] - b * x[0]) / det;
+  q = x[0] * w0 + x[1] * w1;
+  return true;
+}
+
+// min 1/2 x'Bx + g'x on |x| = radius: safeguarded Newton on 1/|x(y)| - 1/radius, x(y) = -(B + yI)^-1 g
+__device__ bool tr_boundary_2d(const double B[3], const double g[2], double radius, double x_out[2]) {
+  const double a = B[0], b = B[1], dd = B[2];
+  const double tr = a + dd, hd = 0.5 * (a - dd);
+  const double disc = sqrt(hd * hd + b * b);
+  const double l1 = 0.5 * tr - disc, l2 = 0.5 * tr + disc;
+  const double gn = sqrt(g[0] * g[0] + g[1] * g[1]);
+  x_out[0] = 0.0;
+  x_out[1] = 0.0;
+  if (!(gn > 0.0) || !(radius > 0.0)) return false;
+  double lo = gn / radius - l2;
+  if (lo < -l1) lo = -l1;
+  double hi = gn / radius - l1;
+  if (!(hi > lo)) hi = lo + fabs(lo) * 1e-12 + 1e-300;
+  double y = 0.0;
+  if (y < lo || y > hi) y = lo;
+  double x[2] = {0.0, 0.0}, n2 = 0.0, q = 0.0;
+  bool have = false;
+  for (int it = 0; it < 100; ++it) {
+    if (!tr2_eval(a, b, dd, g[0], g[1], y, x, n2, q)) {
+      lo = y;
+      y = 0.5 * (lo + hi);
+      if (!(y > lo)) break;
+      continue;
+    }
+    have = true;
+    const double n = sqrt(n2);
+    if (fabs(n - radius) <= 1e-14 * radius) break;
+    if (n > radius) lo = y; else hi = y;
+    double yn = y + ((n - radius) / radius) * (n2 / q);
+    if (!(yn > lo && yn < hi)) yn = 0.5 * (lo + hi);
+    if (yn == y || !(hi > lo)) break;
+    y = yn;
+  }
+  if (!have) return false;
+  const double n = sqrt(n2);
+  if (!(fabs(n - radius) <= 1e-6 * radius)) return false;
+  x_out[0] = x[0];
+  x_out[1] = x[1];
+  return true;
+}
+
+__device__ void dogleg_traditional(Dogleg& S, double step[3]) {
+  const double gnorm = norm3(S.grad), gnn = norm3(S.gn);
+  if (gnn <= S.radius) {
+    for (int i = 0; i < 3; ++i) step[i] = S.gn[i] / S.diag[i];
+    S.step_norm = gnn;
+    return;
+  }
+  if (gnorm * S.alpha >= S.radius) {
+    for (int i = 0; i < 3; ++i) step[i] = (-(S.radius / gnorm) * S.grad[i]) / S.diag[i];
+    S.step_norm = S.radius;
+    return;
+  }
+  const double b_dot_a = -S.alpha * (S.grad[0] * S.gn[0] + S.grad[1] * S.gn[1] + S.grad[2] * S.gn[2]);
+  const double a2 = (S.alpha * gnorm) * (S.alpha * gnorm);
+  const double bma2 = a2 - 2.0 * b_dot_a + gnn * gnn;
+  const double c = b_dot_a - a2;
+  const double dd = sqrt(c * c + bma2 * (S.radius * S.radius - a2));
+  const double beta = (c <= 0.0) ? (dd - c) / bma2 : (S.radius * S.radius - a2) / (dd + c);
+  double dl[3];
+  for (int i = 0; i < 3; ++i) dl[i] = (-S.alpha * (1.0 - beta)) * S.grad[i] + beta * S.gn[i];
+  S.step_norm = norm3(dl);
+  for (int i = 0; i < 3; ++i) step[i] = dl[i] / S.diag[i];
+}
+
+__device__ void dogleg_subspace_step(Dogleg& S, double step[3]) {
+  const double gnn = norm3(S.gn);
+  if (gnn <= S.radius) {
+    for (int i = 0; i < 3; ++i) step[i] = S.gn[i] / S.diag[i];
+    S.step_norm = gnn;
+    return;
+  }
+  if (S.sub1d) {
+    const double gnorm = norm3(S.grad);
+    for (int i = 0; i < 3; ++i) step[i] = (-(S.radius / gnorm) * S.grad[i]) / S.diag[i];
+    S.step_norm = S.radius;
+    return;
+  }
+  double m2[2];
+  if (!tr_boundary_2d(S.sub_B, S.sub_g, S.radius, m2)) {
+    dogleg_traditional(S, step);
+    return;
+  }
+  for (int i = 0; i < 3; ++i) step[i] = (S.U[i][0] * m2[0] + S.U[i][1] * m2[1]) / S.diag[i];
+  S.step_norm = S.radius;
+}
+
+__device__ bool dogleg_compute_step(Dogleg& S, const double Hs[6], const double gs[3], double step[3]) {
+  if (S.reuse) {
+    dogleg_subspace_step(S, step);
+    return true;
+  }
+  S.reuse = 1;
+  const double hd[3] = {Hs[0], Hs[3], Hs[5]};
+  for (int i = 0; i < 3; ++i) {
+    double v = hd[i];
+    if (v < 1e-6) v = 1e-6;
+    if (v > 1e32) v = 1e32;
+    S.diag[i] = sqrt(v);
+  }
+  for (int i = 0; i < 3; ++i) S.grad[i] = gs[i] / S.diag[i];
+  double sg[3];
+  for (int i = 0; i < 3; ++i) sg[i] = S.grad[i] / S.diag[i];
+  const double jg2 = quad3(Hs, sg, sg);
+  S.alpha = (S.grad[0] * S.grad[0] + S.grad[1] * S.grad[1] + S.grad[2] * S.grad[2]) / jg2;
+  bool ok = false;
+  double y[3] = {0.0, 0.0, 0.0};
+  while (S.mu < 1.0) {
+    double A[6] = {Hs[0], Hs[1], Hs[2], Hs[3], Hs[4], Hs[5]};
+    const double sm = sqrt(S.mu);
+    const double l0 = S.diag[0] * sm, l1 = S.diag[1] * sm, l2 = S.diag[2] * sm;
+    A[0] += l0 * l0;
+    A[3] += l1 * l1;
+    A[5] += l2 * l2;
+    if (chol3_solve(A, gs, y)) {
+      ok = true;
+      break;
+    }
+    S.mu *= 10.0;
+  }
+  if (!ok) return false;
+  for (int i = 0; i < 3; ++i) S.gn[i] = -S.diag[i] * y[i];
+  const double n_g = norm3(S.grad), n_n = norm3(S.gn);
+  const bool gfirst = n_g >= n_n;
+  const double na = gfirst ? n_g : n_n;
+  if (!(na > 0.0)) return false;
+  double u0[3], bp[3], A1[3];
+  for (int i = 0; i < 3; ++i) {
+    u0[i] = (gfirst ? S.grad[i] : S.gn[i]) / na;
+    A1[i] = gfirst ? S.gn[i] : S.grad[i];
+  }
+  const double pr = A1[0] * u0[0] + A1[1] * u0[1] + A1[2] * u0[2];
+  for (int i = 0; i < 3; ++i) bp[i] = A1[i] - pr * u0[i];
+  const double nb = norm3(bp);
+  if (!(nb > na * (2.0 * DBL_EPSILON))) {
+    S.sub1d = 1;
+  } else {
+    S.sub1d = 0;
+    double w0[3], w1[3];
+    for (int i = 0; i < 3; ++i) {
+      S.U[i][0] = u0[i];
+      S.U[i][1] = bp[i] / nb;
+    }
+    S.sub_g[0] = S.U[0][0] * S.grad[0] + S.U[1][0] * S.grad[1] + S.U[2][0] * S.grad[2];
+    S.sub_g[1] = S.U[0][1] * S.grad[0] + S.U[1][1] * S.grad[1] + S.U[2][1] * S.grad[2];
+    for (int i = 0; i < 3; ++i) {
+      w0[i] = S.U[i][0] / S.diag[i];
+      w1[i] = S.U[i][1] / S.diag[i];
+    }
+    S.sub_B[0] = quad3(Hs, w0, w0);
+    S.sub_B[1] = quad3(Hs, w0, w1);
+    S.sub_B[2] = quad3(Hs, w1, w1);
+  }
+  dogleg_subspace_step(S, step);
+  return true;
+}
+
+enum { TERM_MAX_ITER = 0, TERM_GRADIENT = 1, TERM_PARAMETER = 2, TERM_FUNCTION = 3, TERM_MIN_RADIUS = 4, TERM_INVALID = 5 };
+
+// One ceres::Solve (TrustRegionMinimizer, Ceres 1.13/1.14 defaults).  Rejected Gauss-Newton steps that
+// would be recomputed identically (radius still above |GN|) are fast-forwarded: the iteration counter and
+// the radius advance exactly as if the identical candidate had been evaluated and rejected again.
+__device__ int solve_tr(const FitPoints& F, const VbModel& M, int max_iter, int lane, double x[3], double& final_cost,
+                        int& iters_out, int& n_evals) {
+  double xc[3] = {x[0], x[1], x[2]};
+  double x_cost, g[3], H[6];
+  eval_jac(F, M, xc, lane, x_cost, g, H);
+  n_evals++;
+  double scale[3];
+  scale[0] = 1.0 / (1.0 + sqrt(H[0]));
+  scale[1] = 1.0 / (1.0 + sqrt(H[3]));
+  scale[2] = 1.0 / (1.0 + sqrt(H[5]));
+  double xnorm = norm3(xc);
+  double best_cost = x_cost, xbest[3] = {xc[0], xc[1], xc[2]};
+  Dogleg S;
+  S.radius = 1e4;
+  S.mu = 1e-8;
+  S.reuse = 0;
+  S.sub1d = 0;
+  S.alpha = 0.0;
+  S.step_norm = 0.0;
+  int iter = 0, invalid = 0, term = TERM_MAX_ITER;
+  bool succ = true;
+  double gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
+  for (;;) {
+    if (iter >= max_iter) { term = TERM_MAX_ITER; break; }
+    if (succ && gmax <= 1e-10) { term = TERM_GRADIENT; break; }
+    if (S.radius <= 1e-32) { term = TERM_MIN_RADIUS; break; }
+    iter++;
+    double Hs[6], gs[3], step[3];
+    Hs[0] = H[0] * scale[0] * scale[0];
+    Hs[1] = H[1] * scale[0] * scale[1];
+    Hs[2] = H[2] * scale[0] * scale[2];
+    Hs[3] = H[3] * scale[1] * scale[1];
+    Hs[4] = H[4] * scale[1] * scale[2];
+    Hs[5] = H[5] * scale[2] * scale[2];
+    for (int i = 0; i < 3; ++i) gs[i] = g[i] * scale[i];
+    const bool ok = dogleg_compute_step(S, Hs, gs, step);
+    bool valid = false;
+    double model_change = 0.0;
+    if (ok) {
+      model_change = -((step[0] * gs[0] + step[1] * gs[1] + step[2] * gs[2]) + 0.5 * quad3(Hs, step, step));
+      valid = model_change > 0.0;
+    }
+    if (!valid) {
+      if (++invalid >= 5) { term = TERM_INVALID; break; }
+      S.mu *= 10.0;
+      S.reuse = 0;
+      succ = false;
+      continue;
+    }
+    invalid = 0;
+    double cand[3];
+    for (int i = 0; i < 3; ++i) cand[i] = xc[i] + step[i] * scale[i];
+    const double cc = eval_cost(F, M, cand, lane);
+    n_evals++;
+    const double d0 = xc[0] - cand[0], d1 = xc[1] - cand[1], d2 = xc[2] - cand[2];
+    const double step_norm = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    if (step_norm <= 1e-8 * (xnorm + 1e-8)) { term = TERM_PARAMETER; break; }
+    const double cost_change = x_cost - cc;
+    if (fabs(cost_change) <= 1e-6 * x_cost) { term = TERM_FUNCTION; break; }
+    const double quality = cost_change / model_change;
+    if (quality > 1e-3) {
+      for (int i = 0; i < 3; ++i) xc[i] = cand[i];
+      xnorm = norm3(xc);
+      eval_jac(F, M, xc, lane, x_cost, g, H);
+      n_evals++;
+      gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
+      succ = true;
+      if (quality < 0.25) S.radius *= 0.5;
+      if (quality > 0.75) S.radius = fmax(S.radius, 3.0 * S.step_norm);
+      S.mu = fmax(1e-8, 2.0 * S.mu / 10.0);
+      S.reuse = 0;
+      if (x_cost < best_cost) {
+        best_cost = x_cost;
+        for (int i = 0; i < 3; ++i) xbest[i] = xc[i];
+      }
+    } else {
+      succ = false;
+      const bool was_gn = norm3(S.gn) <= S.radius;
+      S.radius *= 0.5;
+      S.reuse = 1;
+      if (was_gn) {
+        const double gnn = norm3(S.gn);
+        // the identical Gauss-Newton candidate would be evaluated and rejected again
+        while (iter < max_iter && gnn <= S.radius && S.radius > 1e-32) {
+          iter++;
+          S.radius *= 0.5;
+        }
+      }
+    }
+  }
+  for (int i = 0; i < 3; ++i) x[i] = xbest[i];
+  final_cost = best_cost;
+  iters_out = iter;
+  return term;
+}
+
+__device__ __forceinline__ void rigid_inverse(const float T[16], float O[16]) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) O[4 * r + c] = T[4 * c + r];
+  for (int r = 0; r < 3; ++r) {
+    float v = O[4 * r + 0] * T[3];
+    v = v + O[4 * r + 1] * T[7];
+    v = v + O[4 * r + 2] * T[11];
+    O[4 * r + 3] = -1.0f * v;
+  }
+  O[12] = 0.f; O[13] = 0.f; O[14] = 0.f; O[15] = 1.f;
+}
+
+__global__ void __launch_bounds__(kFitThreads) board_fit_kernel(const Workspace w, const DevParams p) {
+  extern __shared__ unsigned char fit_sm[];
+  __shared__ double s_x[2][3];
+  __shared__ double s_cost[2];
+
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  ilcc2_diag* d = w.diag + f;
+  float* corners = w.corners + (size_t)f * p.ncorners * 3;
+  const int st = d->status;
+  if (st != ILCC2_OK) {
+    for (int i = tid; i < p.ncorners * 3; i += kFitThreads) corners[i] = NAN;
+    if (tid == 0) w.status[f] = st;
+    return;
+  }
+  const unsigned flags = w.flags ? (unsigned)w.flags[f] : w.default_flags;
+  const int n = w.opt_count[f];
+  FitPoints F;
+  F.n = n;
+  const float2* gyz = w.opt_yz + (size_t)f * w.cap;
+  const uint8_t* gwh = w.opt_white + (size_t)f * w.cap;
+  if (n <= kFitSmemPts) {
+    float2* syz = reinterpret_cast<float2*>(fit_sm);
+    uint8_t* swh = fit_sm + sizeof(float2) * kFitSmemPts;
+    for (int k = tid; k < n; k += kFitThreads) {
+      syz[k] = gyz[k];
+      swh[k] = gwh[k];
+    }
+    F.yz = syz;
+    F.white = swh;
+  } else {
+    F.yz = gyz;
+    F.white = gwh;
+  }
+  if (tid < 2) s_cost[tid] = 0.0;
+  __syncthreads();
+
+  const bool autom = (flags & ILCC2_FLAG_AUTO) != 0;
+  VbModel M;
+  M.W = p.W;
+  M.H = p.H;
+  M.inv_g = p.inv_g;
+  M.wg2 = p.wg2;
+  M.hg2 = p.hg2;
+  M.ha = p.huber_a;
+  M.hb = p.huber_b;
+  if (autom || warp == 0) {
+    const int h_first = autom ? warp : 0;
+    const int h_last = autom ? warp : ((flags & ILCC2_FLAG_TOPLEFT_WHITE) ? 1 : 0);
+    double x[3] = {0.0, 0.0, 0.0};
+    for (int h = h_first; h <= h_last; ++h) {  // manual mode: 'd' warm-starts hypothesis 1 from hypothesis 0
+      int evals = 0;
+      double fc = 0.0;
+      for (int phase = 0; phase < 2; ++phase) {
+        M.tlw = h;
+        M.oob = phase == 0 ? 1 : 0;
+        int it = 0;
+        const int term = solve_tr(F, M, p.max_solver_iter, lane, x, fc, it, evals);
+        if (lane == 0) {
+          d->iters[h][phase] = it;
+          d->term[h][phase] = term;
+        }
+      }
+      if (lane == 0) {
+        d->n_evals[h] = evals;
+        d->cost[h] = fc;
+        for (int i = 0; i < 3; ++i) {
+          d->theta_t[h][i] = x[i];
+          s_x[h][i] = x[i];
+        }
+        s_cost[h] = fc;
+      }
+    }
+  }
+  __syncthreads();
+  const int chosen = autom ? ((s_cost[1] < s_cost[0]) ? 1 : 0) : ((flags & ILCC2_FLAG_TOPLEFT_WHITE) ? 1 : 0);
+  // getPCDcorners: lattice -> transOptim^-1 -> transPCA^-1, fp32
+  int W = p.W, H = p.H;
+  if (flags & ILCC2_FLAG_INVERSE) {
+    W = p.H;
+    H = p.W;
+  }
+  const float thf = (float)s_x[chosen][0];
+  const float E = (float)cos((double)thf), Fs = (float)sin((double)thf);
+  const float Topt[16] = {1.f, 0.f, 0.f, 0.f, 0.f, E, -Fs, (float)s_x[chosen][1], 0.f, Fs, E, (float)s_x[chosen][2],
+                          0.f, 0.f, 0.f, 1.f};
+  float pca[16], Ti[16], Pi[16];
+  for (int i = 0; i < 16; ++i) pca[i] = d->pca[i];
+  rigid_inverse(Topt, Ti);
+  rigid_inverse(pca, Pi);
+  for (int k = tid; k < p.ncorners; k += kFitThreads) {
+    const int i = 1 + k / (H - 1), j = 1 + k % (H - 1);
+    const float py = (float)(((double)i - (double)W / 2.0) * p.g);
+    const float pz = (float)(((double)j - (double)H / 2.0) * p.g);
+    float q[3], r[3];
+    xform_pt(Ti, 0.0f, py, pz, q);
+    xform_pt(Pi, q[0], q[1], q[2], r);
+    corners[3 * k + 0] = r[0];
+    corners[3 * k + 1] = r[1];
+    corners[3 * k + 2] = r[2];
+  }
+  if (tid == 0) {
+    d->hyp_chosen = chosen;
+    w.status[f] = ILCC2_OK;
+  }
+}
+
+size_t fit_smem_bytes() { return (sizeof(float2) + 1) * (size_t)kFitSmemPts; }
+
+void launch_board_fit(const Workspace& w, const DevParams& p, cudaStream_t s) {
+  board_fit_kernel<<<w.n_frames, kFitThreads, fit_smem_bytes(), s>>>(w, p);
+}
+
+cudaError_t configure_kernels() {
+  // forward half of the 5x5x5 stencil: the 13 offsets of the 3x3x3 core first, then the 49 outer ones
+  signed char off[62][3];
+  int n = 0;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int dz = -2; dz <= 2; ++dz)
+      for (int dy = -2; dy <= 2; ++dy)
+        for (int dx = -2; dx <= 2; ++dx) {
+          const bool fwd = dz > 0 || (dz == 0 && (dy > 0 || (dy == 0 && dx > 0)));
+          if (!fwd) continue;
+          const bool core = dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1;
+          if ((pass == 0) != core) continue;
+          off[n][0] = (signed char)dx;
+          off[n][1] = (signed char)dy;
+          off[n][2] = (signed char)dz;
+          ++n;
+        }
+  cudaError_t e = cudaMemcpyToSymbol(c_fwd_off, off, sizeof(off));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem_bytes());
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(board_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem_bytes());
+  return e;
+}
+
+}  // namespace ilcc2

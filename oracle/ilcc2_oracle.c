@@ -9,7 +9,7 @@
  * order, so point sets can be compared index-for-index.
  *
  * Double-precision sums that feed decisions (centroid / covariance / normal equations) use one
- * canonical order ("RW-lane strided partial sums + xor butterfly", RW = 128) so that a parallel
+ * canonical order (strided partial sums + xor butterfly, see racc below) so that a parallel
  * implementation can reproduce them; where the reference accumulates in float (PCL) this is a
  * documented deviation (more accurate, <= 3e-6 m on the centroid).
  */
@@ -26,17 +26,24 @@
 /* ------------------------------------------------------------------------------------------ */
 /* canonical reduction                                                                        */
 /* ------------------------------------------------------------------------------------------ */
-#define RW 128
+/* Element k is added to partial sum k mod w (in increasing k); the w partial sums are combined by an xor
+ * butterfly from stride w/2 down to 1.  w = 128 for the centroid / covariance / intensity sums (a 128-thread
+ * CTA reproduces it with one partial per thread), w = 32 for the optimiser's normal equations (one warp). */
+#define RW_MAX 128
+#define RW_BLOCK 128
+#define RW_WARP 32
 
-typedef struct { double p[RW]; } racc;
+typedef struct { double p[RW_MAX]; int w; } racc;
 
-static void racc_zero(racc* a) { memset(a->p, 0, sizeof(a->p)); }
-static inline void racc_add(racc* a, int k, double v) { a->p[k & (RW - 1)] += v; }
+static void racc_zero_w(racc* a, int w) { memset(a->p, 0, sizeof(a->p)); a->w = w; }
+static void racc_zero(racc* a) { racc_zero_w(a, RW_BLOCK); }
+static inline void racc_add(racc* a, int k, double v) { a->p[k & (a->w - 1)] += v; }
 static double racc_total(const racc* a) {
-  double cur[RW], nxt[RW];
+  double cur[RW_MAX], nxt[RW_MAX];
+  const int w = a->w;
   memcpy(cur, a->p, sizeof(cur));
-  for (int s = RW / 2; s >= 1; s >>= 1) {
-    for (int v = 0; v < RW; ++v) nxt[v] = cur[v] + cur[v ^ s];
+  for (int s = w / 2; s >= 1; s >>= 1) {
+    for (int v = 0; v < w; ++v) nxt[v] = cur[v] + cur[v ^ s];
     memcpy(cur, nxt, sizeof(cur));
   }
   return cur[0];
@@ -874,7 +881,7 @@ static double eval_cost(vb_problem* Pb, const double x[3]) {
   const vb_model* M = Pb->M;
   const double c = cos(x[0]), s = sin(x[0]);
   racc a;
-  racc_zero(&a);
+  racc_zero_w(&a, RW_WARP);
   for (int k = 0; k < Pb->n; ++k) {
     double si, sj;
     const double r = vb_point(M, Pb->yz[2 * k], Pb->yz[2 * k + 1], Pb->white[k], c, s, x[1], x[2], &si, &sj);
@@ -890,7 +897,7 @@ static void eval_jac(vb_problem* Pb, const double x[3], double* cost, double g[3
   const vb_model* M = Pb->M;
   const double c = cos(x[0]), s = sin(x[0]);
   racc a[10];
-  for (int q = 0; q < 10; ++q) racc_zero(&a[q]);
+  for (int q = 0; q < 10; ++q) racc_zero_w(&a[q], RW_WARP);
   for (int k = 0; k < Pb->n; ++k) {
     double si, sj;
     const double y = Pb->yz[2 * k], z = Pb->yz[2 * k + 1];
