@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libilcc2_b200.so")
+# ILCC2_LIB overrides the library path (A/B runs of build variants); the default is the in-tree build.
+LIB_PATH = os.environ.get("ILCC2_LIB") or os.path.join(_HERE, "libilcc2_b200.so")
 
 EXPORTS = [
     "ilcc2_version", "ilcc2_default_params", "ilcc2_set_chessboard_param", "ilcc2_create", "ilcc2_destroy",

@@ -213,7 +213,7 @@ int ilcc2_create(const ilcc2_params* params, int device, int max_frames, int max
   ilcc2_handle* h = new ilcc2_handle();
   h->params = p;
   derive(p, h->dp);
-  if ((long long)h->dp.ncx * h->dp.ncy * h->dp.ncz >= (1ll << 31)) {
+  if (h->dp.ncx > 1023 || h->dp.ncy > 1023 || h->dp.ncz > 1023) {
     delete h;
     return fail(nullptr, ILCC2_ERR_INVALID_ARGUMENT, "ROI / cluster_tolerance give too many hash cells");
   }
@@ -243,6 +243,8 @@ int ilcc2_create(const ilcc2_params* params, int device, int max_frames, int max
   A(dev_alloc(h, &w.opt_yz, F * R));
   A(dev_alloc(h, &w.opt_white, F * R));
   A(dev_alloc(h, &w.opt_count, F));
+  w.fit_stride = (h->cap + 31) / 32 + 2ll * h->cap;
+  A(dev_alloc(h, &w.fit_scratch, h->cap > kFitListCap ? F * (size_t)w.fit_stride : 1));
   A(dev_alloc(h, &h->d_clicks, F * 3));
   A(dev_alloc(h, &h->d_flags, F));
   A(dev_alloc(h, &h->d_pdelta, F));
@@ -398,7 +400,7 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
   launch_board_fit(w, h->dp, s);
   CU_TRY(h, stage_done(5));
   h->ev_valid = prof;
-  h->launches += kStages;
+  h->launches += kStages + (h->cap > 65535 ? 1 : 0) + (h->cap > kClusterSmemPts ? 1 : 0);
   CU_TRY(h, cudaGetLastError());
 
   h->last_n_frames = n_frames;

@@ -17,6 +17,8 @@
 #include <float.h>
 #include <math.h>
 
+#include <type_traits>
+
 namespace ilcc2 {
 
 #define FULL 0xffffffffu
@@ -251,14 +253,16 @@ void launch_roi_filter(const Workspace& w, const DevParams& p, cudaStream_t s) {
 // K2  cluster: exact single-linkage components at distance < tol (pcl::EuclideanClusterExtraction) of the
 // ROI points of one frame.  Points are hashed into cells of edge 0.95*tol/sqrt(3): two points of one cell
 // are always linked, and linked points are at most 2 cells apart per axis.  Union-find runs over points
-// (parent of a point = head of its cell to begin with); for every occupied cell and each of the 62
-// "forward" offsets of the 5x5x5 stencil, the two cells are joined as soon as one point pair is closer than
-// tol (skipped when they already share a root).  Near offsets (3x3x3) go first so that most far pairs are
-// already connected when they are visited.  Tables live in shared memory up to kClusterSmemPts points, in
-// a per-frame global scratch beyond that.
+// (parent of a point = head of its cell to begin with); every occupied cell is joined with each occupied
+// cell of the "forward" half of its 5x5x5 neighbourhood as soon as one point pair is closer than tol
+// (skipped when the two already share a root).  The 3x3x3 core goes first so that most outer pairs are
+// already connected when they are visited.
+// Shared-memory layout (frames up to kClusterSmemPts ROI points): open-addressing hash cell -> slot
+// (key, head of the cell's point list), 16-bit next pointers, union-find parents, list of occupied slots,
+// and an occupancy BITMAP with one 32-bit word per (y,z) row of cells, so the five x-neighbours of a row are
+// tested with one load and the hash is only probed for cells that exist.  Larger frames use the same code on
+// a per-frame global scratch without the bitmap.
 // ------------------------------------------------------------------------------------------------
-__constant__ signed char c_fwd_off[62][3];
-
 __device__ __forceinline__ int uf_find(int* par, int x) {
   volatile int* vp = par;
   int cur = vp[x];
@@ -293,42 +297,85 @@ __device__ __forceinline__ unsigned hash_cell(int k) {
   return h ^ (h >> 15);
 }
 
+// cell key: x | y << 10 | z << 20 (each axis < 1024 cells; checked at handle creation)
+__device__ __forceinline__ int pack_cell(int x, int y, int z) { return x | (y << 10) | (z << 20); }
+
+template <typename NxtT>
+__device__ __forceinline__ void join_cells(const float4* __restrict__ P, const int* key, const int* head,
+                                           const NxtT* nxt, int* parent, int mask, int a, int kb, float tol2) {
+  unsigned h = hash_cell(kb) & mask;
+  for (;;) {
+    const int kk = key[h];
+    if (kk == kb) break;
+    if (kk == -1) return;  // not occupied
+    h = (h + 1) & mask;
+  }
+  const int ha = head[a], hb = head[(int)h];
+  if (uf_find(parent, ha) == uf_find(parent, hb)) return;
+  constexpr int kEnd = (NxtT)(-1);
+  for (int pa = ha; pa != kEnd; pa = (int)nxt[pa]) {
+    const float4 qa = __ldg(P + pa);
+    for (int pb = hb; pb != kEnd; pb = (int)nxt[pb]) {
+      const float4 qb = __ldg(P + pb);
+      if (sqdist3(qa.x, qa.y, qa.z, qb.x, qb.y, qb.z) < tol2) {
+        uf_union(parent, pa, pb);
+        return;
+      }
+    }
+  }
+}
+
+// forward half of the 5x5 (dy, dz) rows: row 0 is the cell's own row (dx > 0 only)
+__constant__ signed char c_row_dy[13] = {0, 1, 2, -2, -1, 0, 1, 2, -2, -1, 0, 1, 2};
+__constant__ signed char c_row_dz[13] = {0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2};
+
+template <bool SMEM>
 __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspace w, const DevParams p) {
   constexpr int NT = kClusterThreads;
+  using NxtT = typename std::conditional<SMEM, uint16_t, int>::type;
+  constexpr int kEnd = (NxtT)(-1);
   extern __shared__ int sm[];
   __shared__ int s_warp[NT / 32];
   __shared__ int s_nocc, s_nkept, s_chosen_root;
 
-  const int f = blockIdx.x, tid = threadIdx.x;
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   ilcc2_diag* d = w.diag + f;
   int* sel = w.sel_idx + (size_t)f * w.cap;
   const int M = w.roi_count[f];
+  if ((M <= kClusterSmemPts) != SMEM) return;  // the other instantiation owns this frame
   if (M == 0) {
     if (tid == 0) w.sel_count[f] = 0;
     return;
   }
   int TS;
-  int *key, *head, *nxt, *parent, *occ;
-  if (M <= kClusterSmemPts) {
+  int *key, *head, *parent;
+  NxtT *nxt, *occ;
+  unsigned* bitmap = nullptr;
+  const int nrows = p.ncy * p.ncz;
+  const bool use_bitmap = SMEM && p.ncx <= 32 && nrows <= kClusterBitmapRows;
+  if (SMEM) {
     TS = kClusterSmemSlots;
     key = sm;
     head = key + TS;
-    nxt = head + TS;
-    parent = nxt + kClusterSmemPts;
-    occ = parent + kClusterSmemPts;
+    parent = head + TS;
+    nxt = reinterpret_cast<NxtT*>(parent + kClusterSmemPts);
+    occ = nxt + kClusterSmemPts;
+    bitmap = reinterpret_cast<unsigned*>(occ + kClusterSmemPts);
   } else {
     TS = w.cl_ts;
     int* g = w.cl_scratch + (size_t)f * w.cl_stride;
     key = g;
     head = key + TS;
-    nxt = head + TS;
-    parent = nxt + w.cap;
-    occ = parent + w.cap;
+    parent = head + TS;
+    nxt = reinterpret_cast<NxtT*>(parent + w.cap);
+    occ = nxt + w.cap;
   }
   for (int i = tid; i < TS; i += NT) {
     key[i] = -1;
     head[i] = -1;
   }
+  if (use_bitmap)
+    for (int i = tid; i < nrows; i += NT) bitmap[i] = 0u;
   if (tid == 0) s_nocc = 0;
   __syncthreads();
 
@@ -336,7 +383,7 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
   float lim[6];
   roi_limits(w.clicks + 3 * f, p, lim);
   const int mask = TS - 1;
-  // 1. insert points into the cell hash; per-cell linked lists
+  // 1. insert points into the cell hash; per-cell linked lists; occupancy bitmap
   for (int i = tid; i < M; i += NT) {
     const float4 q = P[i];
     int cx = (int)floorf((q.x - lim[0]) / p.cell);
@@ -345,72 +392,77 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
     cx = min(max(cx, 0), p.ncx - 1);
     cy = min(max(cy, 0), p.ncy - 1);
     cz = min(max(cz, 0), p.ncz - 1);
-    const int k = (cz * p.ncy + cy) * p.ncx + cx;
+    const int k = pack_cell(cx, cy, cz);
     unsigned h = hash_cell(k) & mask;
     for (;;) {
       const int prev = atomicCAS(&key[h], -1, k);
       if (prev == -1) {
-        occ[atomicAdd(&s_nocc, 1)] = (int)h;
+        occ[atomicAdd(&s_nocc, 1)] = (NxtT)h;
+        if (use_bitmap) atomicOr(&bitmap[cz * p.ncy + cy], 1u << cx);
         break;
       }
       if (prev == k) break;
       h = (h + 1) & mask;
     }
-    nxt[i] = atomicExch(&head[h], i);
+    nxt[i] = (NxtT)atomicExch(&head[h], i);
     parent[i] = (int)h;  // slot for now
   }
   __syncthreads();
   for (int i = tid; i < M; i += NT) parent[i] = head[parent[i]];  // same cell => same set
   __syncthreads();
-  // 2. join neighbouring cells
+  // 2. join neighbouring cells: G lanes per cell, lane r of a group owns row r of the forward (dy,dz) rows
   const int nocc = s_nocc;
   const float tol2 = p.tol2;
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
-    const int o_lo = pass == 0 ? 0 : 13, o_n = pass == 0 ? 13 : 49;
-    const int items = nocc * o_n;
-    for (int it = tid; it < items; it += NT) {
-      const int a = occ[it / o_n];
-      const int o = o_lo + it % o_n;
+    // pass 0: the 13 offsets of the 3x3x3 core (5 rows x dx in [-1,1]); pass 1: the 49 outer ones (13 rows)
+    const int G = pass == 0 ? 8 : 16;
+    const int nrow = pass == 0 ? 5 : 13;
+    const int cells_per_iter = NT / G;
+    const int gl = tid % G;
+    int dy = 0, dz = 0;
+    if (gl < nrow) {
+      // pass 0 rows: (0,0) (1,0) (-1,1) (0,1) (1,1);  pass 1: all 13 rows
+      const int r = pass == 0 ? (gl == 0 ? 0 : gl == 1 ? 1 : gl + 2) : gl;
+      dy = c_row_dy[r];
+      dz = c_row_dz[r];
+    }
+    for (int c0 = 0; c0 < nocc; c0 += cells_per_iter) {
+      const int ci = c0 + tid / G;
+      if (ci >= nocc || gl >= nrow) continue;
+      const int a = (int)occ[ci];
       const int ka = key[a];
-      const int ax = ka % p.ncx, ay = (ka / p.ncx) % p.ncy, az = ka / (p.ncx * p.ncy);
-      const int bx = ax + c_fwd_off[o][0], by = ay + c_fwd_off[o][1], bz = az + c_fwd_off[o][2];
-      if (bx < 0 || bx >= p.ncx || by < 0 || by >= p.ncy || bz < 0 || bz >= p.ncz) continue;
-      const int kb = (bz * p.ncy + by) * p.ncx + bx;
-      unsigned h = hash_cell(kb) & mask;
-      int b = -1;
-      for (;;) {
-        const int kk = key[h];
-        if (kk == kb) {
-          b = (int)h;
-          break;
-        }
-        if (kk == -1) break;
-        h = (h + 1) & mask;
+      const int ax = ka & 1023, ay = (ka >> 10) & 1023, az = ka >> 20;
+      const int by = ay + dy, bz = az + dz;
+      if ((unsigned)by >= (unsigned)p.ncy || (unsigned)bz >= (unsigned)p.ncz) continue;
+      // candidate dx set of this row for this pass, as a 5-bit mask (bit dx+2)
+      const bool own = dy == 0 && dz == 0;
+      const bool core_row = dy >= -1 && dy <= 1 && dz <= 1;
+      unsigned want;
+      if (pass == 0)
+        want = own ? 0x08u : 0x0eu;                               // dx = 1 | dx in {-1,0,1}
+      else
+        want = own ? 0x10u : (core_row ? 0x11u : 0x1fu);          // dx = 2 | dx = +-2 | all five
+      if (use_bitmap) {
+        const unsigned row = bitmap[bz * p.ncy + by];
+        const unsigned win = (unsigned)((((unsigned long long)row) << 2) >> ax) & 0x1fu;  // bits ax-2 .. ax+2
+        want &= win;
       }
-      if (b < 0) continue;
-      const int ha = head[a], hb = head[b];
-      if (uf_find(parent, ha) == uf_find(parent, hb)) continue;
-      bool linked = false;
-      for (int pa = ha; pa >= 0 && !linked; pa = nxt[pa]) {
-        const float4 qa = __ldg(P + pa);
-        for (int pb = hb; pb >= 0; pb = nxt[pb]) {
-          const float4 qb = __ldg(P + pb);
-          if (sqdist3(qa.x, qa.y, qa.z, qb.x, qb.y, qb.z) < tol2) {
-            uf_union(parent, pa, pb);
-            linked = true;
-            break;
-          }
-        }
+      while (want) {
+        const int bit = __ffs(want) - 1;
+        want &= want - 1;
+        const int bx = ax + bit - 2;
+        if ((unsigned)bx >= (unsigned)p.ncx) continue;
+        join_cells<NxtT>(P, key, head, nxt, parent, mask, a, pack_cell(bx, by, bz), tol2);
       }
     }
     __syncthreads();
   }
   // 3. roots, sizes, lowest index per component (key/head tables are free now)
-  int* root = nxt;
+  NxtT* root = nxt;
   int* size_of = key;
   int* min_idx = head;
-  int* kept = occ;
+  NxtT* kept = occ;
   for (int i = tid; i < M; i += NT) {
     size_of[i] = 0;
     min_idx[i] = 0x7fffffff;
@@ -419,13 +471,13 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
   __syncthreads();
   for (int i = tid; i < M; i += NT) {
     const int r = uf_find(parent, i);
-    root[i] = r;
+    root[i] = (NxtT)r;
     atomicAdd(&size_of[r], 1);
     atomicMin(&min_idx[r], i);
   }
   __syncthreads();
   for (int i = tid; i < M; i += NT)
-    if (root[i] == i && size_of[i] >= p.min_cl && size_of[i] <= p.max_cl) kept[atomicAdd(&s_nkept, 1)] = i;
+    if ((int)root[i] == i && size_of[i] >= p.min_cl && size_of[i] <= p.max_cl) kept[atomicAdd(&s_nkept, 1)] = (NxtT)i;
   __syncthreads();
   const int nk = s_nkept;
   if (nk == 0) {
@@ -439,11 +491,11 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
   // 4. rank kept clusters: size descending, lowest first index first (PCL leaves ties unspecified)
   int* rank_of = parent;  // indexed by root; parent[] is not needed once root[] is final
   for (int e = tid; e < nk; e += NT) {
-    const int r = kept[e];
+    const int r = (int)kept[e];
     const int sz = size_of[r], mi = min_idx[r];
     int rank = 0;
     for (int j = 0; j < nk; ++j) {
-      const int r2 = kept[j];
+      const int r2 = (int)kept[j];
       const int s2 = size_of[r2];
       if (s2 > sz || (s2 == sz && min_idx[r2] < mi)) ++rank;
     }
@@ -452,15 +504,15 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
   __syncthreads();
   if (tid == 0) {
     const int nn = (int)(w.nn_key[f] & 0xffffffffull);
-    const int rn = root[nn];
+    const int rn = (int)root[nn];
     const bool in = size_of[rn] >= p.min_cl && size_of[rn] <= p.max_cl;
     int rank = in ? rank_of[rn] : 0;
     const int delta = w.pdelta ? (int)w.pdelta[f] : 0;
     if (delta > 0) rank = min(rank + delta, nk - 1);
     if (delta < 0) rank = max(rank + delta, 0);
-    int chosen = kept[0];
+    int chosen = (int)kept[0];
     for (int j = 0; j < nk; ++j)
-      if (rank_of[kept[j]] == rank) chosen = kept[j];
+      if (rank_of[(int)kept[j]] == rank) chosen = (int)kept[j];
     s_chosen_root = chosen;
     d->n_clusters = nk;
     d->click_in_cluster = in ? 1 : 0;
@@ -473,19 +525,26 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
   int total = 0;
   for (int base = 0; base < M; base += NT) {
     const int i = base + tid;
-    const bool pr = i < M && root[i] == chosen;
+    const bool pr = i < M && (int)root[i] == chosen;
     int tile_total;
     const int off = block_ordered_offset<NT>(pr, s_warp, tile_total);
     if (pr) sel[total + off] = i;
     total += tile_total;
   }
   if (tid == 0) w.sel_count[f] = total;
+  (void)kEnd;
+  (void)lane;
+  (void)warp;
 }
 
-size_t cluster_smem_bytes() { return sizeof(int) * (2 * kClusterSmemSlots + 3 * kClusterSmemPts); }
+size_t cluster_smem_bytes() {
+  return sizeof(int) * (2 * kClusterSmemSlots + kClusterSmemPts) + sizeof(uint16_t) * 2 * kClusterSmemPts +
+         sizeof(unsigned) * kClusterBitmapRows;
+}
 
 void launch_cluster(const Workspace& w, const DevParams& p, cudaStream_t s) {
-  cluster_kernel<<<w.n_frames, kClusterThreads, cluster_smem_bytes(), s>>>(w, p);
+  cluster_kernel<true><<<w.n_frames, kClusterThreads, cluster_smem_bytes(), s>>>(w, p);
+  if (w.cap > kClusterSmemPts) cluster_kernel<false><<<w.n_frames, kClusterThreads, 0, s>>>(w, p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1144,142 +1203,233 @@ void launch_pca_gray(const Workspace& w, const DevParams& p, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------
 // K5  board_fit: the virtual-chessboard pose optimisation (one ceres::Solve per phase in the reference).
-// One warp per (frame, colour hypothesis).  Every lane owns the points k = lane (mod 32); residuals and
-// the 3-column Jacobian are evaluated in fp64, cost / J^T r / J^T J are reduced by a 32-lane xor butterfly,
-// and the 3x3 trust-region dogleg step (subspace dogleg, as configured at Optimization.cpp:145-149) is
-// computed redundantly by all lanes, so a solve needs no shared-memory traffic and no block barrier.
+// One warp per (frame, colour hypothesis); both warps of a CTA share the frame's points in shared memory
+// (float2 y',z' + one colour bit per point).  A residual evaluation has two passes:
+//   classify (fp32, every point): which virtual cell does the point fall in, with an error margin derived from
+//     a forward error bound of the fp32 arithmetic.  Points that are CERTAINLY inside a cell of their own
+//     colour (about 90 %) have a residual of exactly zero and are dropped; the others are compacted (ballot)
+//     into two dense lists: L1 = colour mismatch or not certain (near a cell border / the board edge),
+//     L2 = certainly outside the board (only contributes while useOutofBoard is on).
+//   evaluate (fp64, listed points only, all lanes busy): the exact residual of Optimization.h:31-107, Huber
+//     cost, and -- when the step is accepted -- the 3-column Jacobian, J^T r and J^T J, from the SAME lists
+//     (Ceres evaluates the accepted point a second time; here nothing is recomputed for the dropped points).
+// Sums are lane-strided over the lists + xor butterfly: deterministic, but grouped differently from the CPU
+// oracle's sums (agreement ~1e-15 relative, see tests).  The 3x3 dogleg step (subspace dogleg,
+// Optimization.cpp:145-149) is computed redundantly by all lanes: no barrier inside a solve.
 // ------------------------------------------------------------------------------------------------
 struct VbModel {
-  int W, H, tlw, oob;
-  double inv_g, wg2, hg2, ha, hb;
+  int tlw;
+  double Wd, Hd, inv_g, wg2, hg2, ha, hb, two_ha;
+  float ymax_zmax;  // max|y'| + max|z'| over the frame's points (for the fp32 error bound)
 };
 
-__device__ __forceinline__ double vb_point(const VbModel& M, double y, double z, int white, double c, double s,
-                                           double ty, double tz, double& si, double& sj) {
+template <typename IdxT>
+struct FitPts {
+  const float2* yz;
+  const uint32_t* wbits;
+  int n;
+  IdxT* list;    // this warp's list buffer: L1 grows up from 0, L2 grows down from list_cap-1
+  int list_cap;  // entries; also the chunk length (a chunk of list_cap points can never overflow it)
+};
+
+// exact residual of one point (Optimization.h:31-107) with the signs of its autodiff Jacobian, branch-free
+// except for the (warp-uniform) useOutofBoard switch. wx = laser_white ^ topleftWhite.
+__device__ __forceinline__ double vb_eval(const VbModel& M, bool oob, double y, double z, unsigned wx, double c,
+                                          double s, double ty, double tz, double& si, double& sj) {
   const double yy = (y * c - z * s) + ty;
   const double zz = (z * c + y * s) + tz;
   const double fi = (yy + M.wg2) * M.inv_g;
   const double fj = (zz + M.hg2) * M.inv_g;
-  si = 0.0;
-  sj = 0.0;
-  if (fi > 0.0 && fi < (double)M.W && fj > 0.0 && fj < (double)M.H) {
-    const double ifl = floor(fi), jfl = floor(fj);
-    const int same = ((((int)ifl) ^ ((int)jfl)) & 1) == 0;
-    const int cell_white = same ? M.tlw : !M.tlw;
-    if (white == cell_white) return 0.0;
-    double ei, ej;
-    const double di = fi - ifl, dj = fj - jfl;
-    if (di > 0.5) {
-      ei = ceil(fi) - fi;
-      si = -1.0;
-    } else {
-      ei = di;
-      si = 1.0;
-    }
-    if (dj > 0.5) {
-      ej = ceil(fj) - fj;
-      sj = -1.0;
-    } else {
-      ej = dj;
-      sj = 1.0;
-    }
-    return ei + ej;
+  const bool in = fi > 0.0 && fi < M.Wd && fj > 0.0 && fj < M.Hd;
+  // floor for 0 <= f < 2^51: (f + 2^52) - 2^52 rounds to the nearest integer, step back if it went up
+  const double kMagic = 4503599627370496.0;
+  const double ti = fi + kMagic, tj = fj + kMagic;
+  const double ri = ti - kMagic, rj = tj - kMagic;
+  const bool ci = ri > fi, cj = rj > fj;
+  const double ifl = ci ? ri - 1.0 : ri;
+  const double jfl = cj ? rj - 1.0 : rj;
+  const unsigned par = ((unsigned)__double2loint(ti) ^ (unsigned)__double2loint(tj) ^ (unsigned)ci ^ (unsigned)cj) & 1u;
+  const bool mismatch = ((wx ^ par) & 1u) != 0u;  // laser colour != colour of the virtual cell
+  const double di = fi - ifl, dj = fj - jfl;
+  const bool bi = di > 0.5, bj = dj > 0.5;
+  const double ei = bi ? (ifl + 1.0) - fi : di;
+  const double ej = bj ? (jfl + 1.0) - fj : dj;
+  double r = mismatch ? ei + ej : 0.0;
+  si = bi ? -1.0 : 1.0;
+  sj = bj ? -1.0 : 1.0;
+  if (oob) {
+    const double fiw = fi - M.Wd, fjh = fj - M.Hd;
+    const double a0 = fabs(fi), a1 = fabs(fiw);
+    const double b0 = fabs(fj), b1 = fabs(fjh);
+    const bool li = a0 < a1, lj = b0 < b1;
+    const double ro = (li ? a0 : a1) + (lj ? b0 : b1);
+    const double sio = (li ? fi : fiw) < 0.0 ? -1.0 : 1.0;
+    const double sjo = (lj ? fj : fjh) < 0.0 ? -1.0 : 1.0;
+    r = in ? r : ro;
+    si = in ? si : sio;
+    sj = in ? sj : sjo;
+  } else {
+    r = in ? r : 0.0;
   }
-  if (M.oob) {
-    double ei, ej;
-    const double a0 = fabs(fi), a1 = fabs(fi - (double)M.W);
-    if (a0 < a1) {
-      ei = a0;
-      si = fi < 0.0 ? -1.0 : 1.0;
-    } else {
-      ei = a1;
-      si = (fi - (double)M.W) < 0.0 ? -1.0 : 1.0;
-    }
-    const double b0 = fabs(fj), b1 = fabs(fj - (double)M.H);
-    if (b0 < b1) {
-      ej = b0;
-      sj = fj < 0.0 ? -1.0 : 1.0;
-    } else {
-      ej = b1;
-      sj = (fj - (double)M.H) < 0.0 ? -1.0 : 1.0;
-    }
-    return ei + ej;
-  }
-  return 0.0;
+  return r;
 }
+
+// residual (and Jacobian signs) of a point that is certainly outside the board: the useOutofBoard branch,
+// Optimization.h:86-101 -- same expressions as the corresponding part of vb_eval.
+__device__ __forceinline__ double vb_eval_out(const VbModel& M, double y, double z, double c, double s, double ty,
+                                              double tz, double& si, double& sj) {
+  const double yy = (y * c - z * s) + ty;
+  const double zz = (z * c + y * s) + tz;
+  const double fi = (yy + M.wg2) * M.inv_g;
+  const double fj = (zz + M.hg2) * M.inv_g;
+  const double fiw = fi - M.Wd, fjh = fj - M.Hd;
+  const double a0 = fabs(fi), a1 = fabs(fiw);
+  const double b0 = fabs(fj), b1 = fabs(fjh);
+  const bool li = a0 < a1, lj = b0 < b1;
+  si = (li ? fi : fiw) < 0.0 ? -1.0 : 1.0;
+  sj = (lj ? fj : fjh) < 0.0 ? -1.0 : 1.0;
+  return (li ? a0 : a1) + (lj ? b0 : b1);
+}
+
+// IEEE double division / square root expand to ~50 instructions each at every use; the scalar solver below has
+// ~100 of them.  One out-of-line copy keeps the kernel image (and its instruction-cache footprint) small.
+__device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+__device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
+
+// sincos() inlines a large slow path; keep one copy of it in the kernel
+__device__ __noinline__ void sincos_once(double x, double* s, double* c) { sincos(x, s, c); }
 
 __device__ __forceinline__ double huber_cost(const VbModel& M, double r) {
-  const double s = r * r;
-  if (s > M.hb) return 0.5 * (2.0 * M.ha * r - M.hb);
-  return 0.5 * s;
+  const double sq = r * r;
+  return (sq > M.hb) ? 0.5 * (M.two_ha * r - M.hb) : 0.5 * sq;
 }
 
-struct FitPoints {
-  const float2* yz;
-  const uint8_t* white;
-  int n;
-};
-
-__device__ double eval_cost(const FitPoints& F, const VbModel& M, const double x[3], int lane) {
-  double s, c;
-  sincos(x[0], &s, &c);
-  double acc = 0.0;
-  for (int k = lane; k < F.n; k += 32) {
-    const float2 q = F.yz[k];
-    double si, sj;
-    const double r = vb_point(M, (double)q.x, (double)q.y, F.white[k], c, s, x[1], x[2], si, sj);
-    if (r != 0.0) acc += huber_cost(M, r);
-  }
-  return warp_butterfly(acc);
-}
-
-__device__ void eval_jac(const FitPoints& F, const VbModel& M, const double x[3], int lane, double& cost,
-                         double g[3], double H[6]) {
-  double s, c;
-  sincos(x[0], &s, &c);
-  double a[10];
-#pragma unroll
-  for (int q = 0; q < 10; ++q) a[q] = 0.0;
-  for (int k = lane; k < F.n; k += 32) {
-    const float2 qq = F.yz[k];
-    const double y = (double)qq.x, z = (double)qq.y;
-    double si, sj;
-    const double r = vb_point(M, y, z, F.white[k], c, s, x[1], x[2], si, sj);
-    if (r == 0.0) continue;
-    const double dyy = -(y * s) - (z * c);
-    const double dzz = (y * c) - (z * s);
-    double j0 = (si * dyy) * M.inv_g + (sj * dzz) * M.inv_g;
-    double j1 = si * M.inv_g;
-    double j2 = sj * M.inv_g;
-    double rr = r;
-    const double sq = r * r;
-    if (sq > M.hb) {
-      const double rho1 = M.ha / r;
-      const double sc = sqrt(rho1);
-      j0 *= sc;
-      j1 *= sc;
-      j2 *= sc;
-      rr = sc * r;
+// fp32 classification of points [k0, k1) (k1 - k0 <= list_cap) at pose (c, s, ty, tz) -> lists L1 (up), L2 (down).
+//   fi = ((y c - z s) + ty + W g/2) / g  evaluated with two FMAs; forward error bound 5u(|y|+|z|+|t|)/g with
+//   u = 2^-24 (+1 rounding for the pre-scaled constants): 8u is used, times a safety factor 4 -> margin m.
+//   A point is CERTAINLY inside cell (floor fi, floor fj) of the board when both coordinates are at least m away
+//   from every integer and from the board edges; it is CERTAINLY outside when one coordinate is m beyond an edge.
+template <typename IdxT>
+__device__ __forceinline__ void classify_pass(const float2* __restrict__ yz, const uint32_t* __restrict__ wbits,
+                                              IdxT* list, int list_cap, const VbModel& M, bool oob, double c, double s,
+                                              double ty, double tz, int lane, int k0, int k1, int& n1, int& n2) {
+  const float ig = (float)M.inv_g;
+  const float cg = (float)c * ig, sg = (float)s * ig;
+  const float tyw = (float)(ty + M.wg2) * ig, tzh = (float)(tz + M.hg2) * ig;
+  const float Wh = 0.5f * (float)M.Wd, Hh = 0.5f * (float)M.Hd;
+  const float bound = (8.0f * 5.9604645e-8f) * (M.ymax_zmax * ig + fmaxf(fabsf(tyw), fabsf(tzh)));
+  const float m = 4.0f * bound + 1e-6f;
+  const float kMagicF = 12582912.0f;  // 1.5 * 2^23: (f + magic) - magic = rint(f) for |f| < 2^22
+  const unsigned tlw = (unsigned)M.tlw;
+  int c1 = 0, c2 = 0;
+  const unsigned lt = (1u << lane) - 1u;
+#ifndef CLS_UNROLL
+#define CLS_UNROLL 1
+#endif
+  constexpr int kClsUnroll = CLS_UNROLL;
+#pragma unroll kClsUnroll
+  for (int base = k0; base < k1; base += 32) {
+    const int k = base + lane;
+    const bool valid = k < k1;
+    const float2 q = __ldg(yz + (valid ? k : k0));
+    const unsigned wword = wbits[base >> 5];
+    const float fi = fmaf(q.x, cg, fmaf(-q.y, sg, tyw));
+    const float fj = fmaf(q.y, cg, fmaf(q.x, sg, tzh));
+    const float ti = fi + kMagicF, tj = fj + kMagicF;
+    const float di = fi - (ti - kMagicF), dj = fj - (tj - kMagicF);  // signed distance to the nearest integer
+    // cell parity: parity(rint) ^ (d < 0)
+    const unsigned par = (__float_as_uint(ti) ^ __float_as_uint(tj) ^ ((__float_as_uint(di) ^ __float_as_uint(dj)) >> 31)) & 1u;
+    const bool interior = fminf(fabsf(di), fabsf(dj)) >= m;
+    const float edge = fmaxf(fabsf(fi - Wh) - Wh, fabsf(fj - Hh) - Hh);  // < 0 inside the board, > 0 outside
+    const bool certain_in = interior && edge <= -m;
+    const bool outb = edge >= m;
+    const bool mism = ((((wword >> lane) ^ tlw ^ par) & 1u) != 0u);
+    const bool is1 = valid && (certain_in ? mism : !outb);
+    const unsigned b1 = __ballot_sync(FULL, is1);
+    if (is1) list[c1 + __popc(b1 & lt)] = (IdxT)k;
+    c1 += __popc(b1);
+    if (oob) {
+      const bool is2 = valid && outb;
+      const unsigned b2 = __ballot_sync(FULL, is2);
+      if (is2) list[list_cap - 1 - (c2 + __popc(b2 & lt))] = (IdxT)k;
+      c2 += __popc(b2);
     }
-    a[0] += huber_cost(M, r);
-    a[1] += j0 * rr;
-    a[2] += j1 * rr;
-    a[3] += j2 * rr;
-    a[4] += j0 * j0;
-    a[5] += j0 * j1;
-    a[6] += j0 * j2;
-    a[7] += j1 * j1;
-    a[8] += j1 * j2;
-    a[9] += j2 * j2;
   }
-#pragma unroll
-  for (int q = 0; q < 10; ++q) a[q] = warp_butterfly(a[q]);
-  cost = a[0];
-  g[0] = a[1];
-  g[1] = a[2];
-  g[2] = a[3];
-#pragma unroll
-  for (int q = 0; q < 6; ++q) H[q] = a[4 + q];
+  __syncwarp();
+  n1 = c1;
+  n2 = c2;
+}
+
+// accumulate one evaluated point: Huber cost (want_jac false) or J^T r / J^T J with the Huber corrector
+__device__ __forceinline__ void accumulate_point(const VbModel& M, bool want_jac, double y, double z, double c, double s,
+                                                 double r, double si, double sj, double (&a)[9]) {
+  if (!want_jac) {
+    a[0] += huber_cost(M, r);
+    return;
+  }
+  const double dyy = -(y * s) - (z * c);
+  const double dzz = (y * c) - (z * s);
+  double j0v = (si * dyy) * M.inv_g + (sj * dzz) * M.inv_g;
+  double j1 = si * M.inv_g;
+  double j2 = sj * M.inv_g;
+  double rr = r;
+  const bool big = r * r > M.hb;
+  if (__any_sync(FULL, big)) {  // Huber corrector: scale row and residual by sqrt(rho') = sqrt(a / r)
+    const double rho1 = ddiv(M.ha, big ? r : 1.0);
+    const double sc = big ? dsqrt(rho1) : 1.0;
+    j0v *= sc;
+    j1 *= sc;
+    j2 *= sc;
+    rr = sc * r;
+  }
+  if (r == 0.0) {
+    j0v = 0.0;
+    j1 = 0.0;
+    j2 = 0.0;
+  }
+  a[0] += j0v * rr;
+  a[1] += j1 * rr;
+  a[2] += j2 * rr;
+  a[3] += j0v * j0v;
+  a[4] += j0v * j1;
+  a[5] += j0v * j2;
+  a[6] += j1 * j1;
+  a[7] += j1 * j2;
+  a[8] += j2 * j2;
+}
+
+// exact fp64 evaluation of the listed points (all lanes busy; uniform trip counts because of __any_sync).
+// want_jac = false: a[0] += Huber cost.  want_jac = true: a[0..2] += J^T r, a[3..8] += J^T J.
+template <typename IdxT>
+__device__ __forceinline__ void list_pass(const float2* __restrict__ yz, const uint32_t* __restrict__ wbits,
+                                          const IdxT* list, int list_cap, const VbModel& M, bool oob, bool want_jac,
+                                          double c, double s, double ty, double tz, int lane, int n1, int n2,
+                                          double (&a)[9]) {
+  for (int e0 = 0; e0 < n1; e0 += 32) {  // L1: colour mismatch or not certain -> full residual
+    const int e = e0 + lane;
+    const bool act = e < n1;
+    const int k = act ? (int)list[e] : 0;
+    const float2 q = __ldg(yz + k);
+    const unsigned wx = ((wbits[k >> 5] >> (k & 31)) & 1u) ^ (unsigned)M.tlw;
+    const double y = (double)q.x, z = (double)q.y;
+    double si, sj;
+    double r = vb_eval(M, oob, y, z, wx, c, s, ty, tz, si, sj);
+    if (!act) r = 0.0;
+    accumulate_point(M, want_jac, y, z, c, s, r, si, sj, a);
+  }
+  if (oob) {
+    for (int e0 = 0; e0 < n2; e0 += 32) {  // L2: certainly outside the board -> distance to the nearest edges
+      const int e = e0 + lane;
+      const bool act = e < n2;
+      const int k = act ? (int)list[list_cap - 1 - e] : 0;
+      const float2 q = yz[k];
+      const double y = (double)q.x, z = (double)q.y;
+      double si, sj;
+      double r = vb_eval_out(M, y, z, c, s, ty, tz, si, sj);
+      if (!act) r = 0.0;
+      accumulate_point(M, want_jac, y, z, c, s, r, si, sj, a);
+    }
+  }
 }
 
 // --- 3x3 trust-region machinery (all lanes execute it redundantly on identical inputs) ---
@@ -1292,7 +1442,7 @@ struct Dogleg {
   double step_norm;
 };
 
-__device__ __forceinline__ double norm3(const double v[3]) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+__device__ __forceinline__ double norm3(const double v[3]) { return dsqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
 
 __device__ __forceinline__ double quad3(const double H[6], const double u[3], const double v[3]) {
   const double h0 = H[0] * v[0] + H[1] * v[1] + H[2] * v[2];
@@ -1303,22 +1453,22 @@ __device__ __forceinline__ double quad3(const double H[6], const double u[3], co
 
 __device__ bool chol3_solve(const double A[6], const double b[3], double x[3]) {
   if (!(A[0] > 0.0)) return false;
-  const double l00 = sqrt(A[0]);
-  const double l10 = A[1] / l00;
-  const double l20 = A[2] / l00;
+  const double l00 = dsqrt(A[0]);
+  const double l10 = ddiv(A[1], l00);
+  const double l20 = ddiv(A[2], l00);
   double t = A[3] - l10 * l10;
   if (!(t > 0.0)) return false;
-  const double l11 = sqrt(t);
-  const double l21 = (A[4] - l20 * l10) / l11;
+  const double l11 = dsqrt(t);
+  const double l21 = ddiv(A[4] - l20 * l10, l11);
   t = A[5] - l20 * l20 - l21 * l21;
   if (!(t > 0.0)) return false;
-  const double l22 = sqrt(t);
-  const double y0 = b[0] / l00;
-  const double y1 = (b[1] - l10 * y0) / l11;
-  const double y2 = (b[2] - l20 * y0 - l21 * y1) / l22;
-  x[2] = y2 / l22;
-  x[1] = (y1 - l21 * x[2]) / l11;
-  x[0] = (y0 - l10 * x[1] - l20 * x[2]) / l00;
+  const double l22 = dsqrt(t);
+  const double y0 = ddiv(b[0], l00);
+  const double y1 = ddiv(b[1] - l10 * y0, l11);
+  const double y2 = ddiv(b[2] - l20 * y0 - l21 * y1, l22);
+  x[2] = ddiv(y2, l22);
+  x[1] = ddiv(y1 - l21 * x[2], l11);
+  x[0] = ddiv(y0 - l10 * x[1] - l20 * x[2], l00);
   return isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]);
 }
 
@@ -1327,28 +1477,28 @@ __device__ bool tr2_eval(double a, double b, double dd, double g0, double g1, do
   const double ay = a + y, dy = dd + y;
   const double det = ay * dy - b * b;
   if (!(ay > 0.0) || !(det > 0.0)) return false;
-  x[0] = -(dy * g0 - b * g1) / det;
-  x[1] = -(ay * g1 - b * g0) / det;
+  x[0] = ddiv(-(dy * g0 - b * g1), det);
+  x[1] = ddiv(-(ay * g1 - b * g0), det);
   n2 = x[0] * x[0] + x[1] * x[1];
-  const double w0 = (dy * x[0] - b * x[1]) / det;
-  const double w1 = (ay * x[1] - b * x[0]) / det;
+  const double w0 = ddiv(dy * x[0] - b * x[1], det);
+  const double w1 = ddiv(ay * x[1] - b * x[0], det);
   q = x[0] * w0 + x[1] * w1;
   return true;
 }
 
 // min 1/2 x'Bx + g'x on |x| = radius: safeguarded Newton on 1/|x(y)| - 1/radius, x(y) = -(B + yI)^-1 g
-__device__ bool tr_boundary_2d(const double B[3], const double g[2], double radius, double x_out[2]) {
+__device__ __noinline__ bool tr_boundary_2d(const double B[3], const double g[2], double radius, double x_out[2]) {
   const double a = B[0], b = B[1], dd = B[2];
   const double tr = a + dd, hd = 0.5 * (a - dd);
-  const double disc = sqrt(hd * hd + b * b);
+  const double disc = dsqrt(hd * hd + b * b);
   const double l1 = 0.5 * tr - disc, l2 = 0.5 * tr + disc;
-  const double gn = sqrt(g[0] * g[0] + g[1] * g[1]);
+  const double gn = dsqrt(g[0] * g[0] + g[1] * g[1]);
   x_out[0] = 0.0;
   x_out[1] = 0.0;
   if (!(gn > 0.0) || !(radius > 0.0)) return false;
-  double lo = gn / radius - l2;
+  double lo = ddiv(gn, radius) - l2;
   if (lo < -l1) lo = -l1;
-  double hi = gn / radius - l1;
+  double hi = ddiv(gn, radius) - l1;
   if (!(hi > lo)) hi = lo + fabs(lo) * 1e-12 + 1e-300;
   double y = 0.0;
   if (y < lo || y > hi) y = lo;
@@ -1362,16 +1512,16 @@ __device__ bool tr_boundary_2d(const double B[3], const double g[2], double radi
       continue;
     }
     have = true;
-    const double n = sqrt(n2);
+    const double n = dsqrt(n2);
     if (fabs(n - radius) <= 1e-14 * radius) break;
     if (n > radius) lo = y; else hi = y;
-    double yn = y + ((n - radius) / radius) * (n2 / q);
+    double yn = y + ddiv(n - radius, radius) * ddiv(n2, q);
     if (!(yn > lo && yn < hi)) yn = 0.5 * (lo + hi);
     if (yn == y || !(hi > lo)) break;
     y = yn;
   }
   if (!have) return false;
-  const double n = sqrt(n2);
+  const double n = dsqrt(n2);
   if (!(fabs(n - radius) <= 1e-6 * radius)) return false;
   x_out[0] = x[0];
   x_out[1] = x[1];
@@ -1381,12 +1531,12 @@ __device__ bool tr_boundary_2d(const double B[3], const double g[2], double radi
 __device__ void dogleg_traditional(Dogleg& S, double step[3]) {
   const double gnorm = norm3(S.grad), gnn = norm3(S.gn);
   if (gnn <= S.radius) {
-    for (int i = 0; i < 3; ++i) step[i] = S.gn[i] / S.diag[i];
+    for (int i = 0; i < 3; ++i) step[i] = ddiv(S.gn[i], S.diag[i]);
     S.step_norm = gnn;
     return;
   }
   if (gnorm * S.alpha >= S.radius) {
-    for (int i = 0; i < 3; ++i) step[i] = (-(S.radius / gnorm) * S.grad[i]) / S.diag[i];
+    for (int i = 0; i < 3; ++i) step[i] = ddiv(-ddiv(S.radius, gnorm) * S.grad[i], S.diag[i]);
     S.step_norm = S.radius;
     return;
   }
@@ -1394,24 +1544,24 @@ __device__ void dogleg_traditional(Dogleg& S, double step[3]) {
   const double a2 = (S.alpha * gnorm) * (S.alpha * gnorm);
   const double bma2 = a2 - 2.0 * b_dot_a + gnn * gnn;
   const double c = b_dot_a - a2;
-  const double dd = sqrt(c * c + bma2 * (S.radius * S.radius - a2));
-  const double beta = (c <= 0.0) ? (dd - c) / bma2 : (S.radius * S.radius - a2) / (dd + c);
+  const double dd = dsqrt(c * c + bma2 * (S.radius * S.radius - a2));
+  const double beta = (c <= 0.0) ? ddiv(dd - c, bma2) : ddiv(S.radius * S.radius - a2, dd + c);
   double dl[3];
   for (int i = 0; i < 3; ++i) dl[i] = (-S.alpha * (1.0 - beta)) * S.grad[i] + beta * S.gn[i];
   S.step_norm = norm3(dl);
-  for (int i = 0; i < 3; ++i) step[i] = dl[i] / S.diag[i];
+  for (int i = 0; i < 3; ++i) step[i] = ddiv(dl[i], S.diag[i]);
 }
 
 __device__ void dogleg_subspace_step(Dogleg& S, double step[3]) {
   const double gnn = norm3(S.gn);
   if (gnn <= S.radius) {
-    for (int i = 0; i < 3; ++i) step[i] = S.gn[i] / S.diag[i];
+    for (int i = 0; i < 3; ++i) step[i] = ddiv(S.gn[i], S.diag[i]);
     S.step_norm = gnn;
     return;
   }
   if (S.sub1d) {
     const double gnorm = norm3(S.grad);
-    for (int i = 0; i < 3; ++i) step[i] = (-(S.radius / gnorm) * S.grad[i]) / S.diag[i];
+    for (int i = 0; i < 3; ++i) step[i] = ddiv(-ddiv(S.radius, gnorm) * S.grad[i], S.diag[i]);
     S.step_norm = S.radius;
     return;
   }
@@ -1420,11 +1570,11 @@ __device__ void dogleg_subspace_step(Dogleg& S, double step[3]) {
     dogleg_traditional(S, step);
     return;
   }
-  for (int i = 0; i < 3; ++i) step[i] = (S.U[i][0] * m2[0] + S.U[i][1] * m2[1]) / S.diag[i];
+  for (int i = 0; i < 3; ++i) step[i] = ddiv(S.U[i][0] * m2[0] + S.U[i][1] * m2[1], S.diag[i]);
   S.step_norm = S.radius;
 }
 
-__device__ bool dogleg_compute_step(Dogleg& S, const double Hs[6], const double gs[3], double step[3]) {
+__device__ __noinline__ bool dogleg_compute_step(Dogleg& S, const double Hs[6], const double gs[3], double step[3]) {
   if (S.reuse) {
     dogleg_subspace_step(S, step);
     return true;
@@ -1435,18 +1585,18 @@ __device__ bool dogleg_compute_step(Dogleg& S, const double Hs[6], const double 
     double v = hd[i];
     if (v < 1e-6) v = 1e-6;
     if (v > 1e32) v = 1e32;
-    S.diag[i] = sqrt(v);
+    S.diag[i] = dsqrt(v);
   }
-  for (int i = 0; i < 3; ++i) S.grad[i] = gs[i] / S.diag[i];
+  for (int i = 0; i < 3; ++i) S.grad[i] = ddiv(gs[i], S.diag[i]);
   double sg[3];
-  for (int i = 0; i < 3; ++i) sg[i] = S.grad[i] / S.diag[i];
+  for (int i = 0; i < 3; ++i) sg[i] = ddiv(S.grad[i], S.diag[i]);
   const double jg2 = quad3(Hs, sg, sg);
-  S.alpha = (S.grad[0] * S.grad[0] + S.grad[1] * S.grad[1] + S.grad[2] * S.grad[2]) / jg2;
+  S.alpha = ddiv(S.grad[0] * S.grad[0] + S.grad[1] * S.grad[1] + S.grad[2] * S.grad[2], jg2);
   bool ok = false;
   double y[3] = {0.0, 0.0, 0.0};
   while (S.mu < 1.0) {
     double A[6] = {Hs[0], Hs[1], Hs[2], Hs[3], Hs[4], Hs[5]};
-    const double sm = sqrt(S.mu);
+    const double sm = dsqrt(S.mu);
     const double l0 = S.diag[0] * sm, l1 = S.diag[1] * sm, l2 = S.diag[2] * sm;
     A[0] += l0 * l0;
     A[3] += l1 * l1;
@@ -1465,7 +1615,7 @@ __device__ bool dogleg_compute_step(Dogleg& S, const double Hs[6], const double 
   if (!(na > 0.0)) return false;
   double u0[3], bp[3], A1[3];
   for (int i = 0; i < 3; ++i) {
-    u0[i] = (gfirst ? S.grad[i] : S.gn[i]) / na;
+    u0[i] = ddiv(gfirst ? S.grad[i] : S.gn[i], na);
     A1[i] = gfirst ? S.gn[i] : S.grad[i];
   }
   const double pr = A1[0] * u0[0] + A1[1] * u0[1] + A1[2] * u0[2];
@@ -1478,13 +1628,13 @@ __device__ bool dogleg_compute_step(Dogleg& S, const double Hs[6], const double 
     double w0[3], w1[3];
     for (int i = 0; i < 3; ++i) {
       S.U[i][0] = u0[i];
-      S.U[i][1] = bp[i] / nb;
+      S.U[i][1] = ddiv(bp[i], nb);
     }
     S.sub_g[0] = S.U[0][0] * S.grad[0] + S.U[1][0] * S.grad[1] + S.U[2][0] * S.grad[2];
     S.sub_g[1] = S.U[0][1] * S.grad[0] + S.U[1][1] * S.grad[1] + S.U[2][1] * S.grad[2];
     for (int i = 0; i < 3; ++i) {
-      w0[i] = S.U[i][0] / S.diag[i];
-      w1[i] = S.U[i][1] / S.diag[i];
+      w0[i] = ddiv(S.U[i][0], S.diag[i]);
+      w1[i] = ddiv(S.U[i][1], S.diag[i]);
     }
     S.sub_B[0] = quad3(Hs, w0, w0);
     S.sub_B[1] = quad3(Hs, w0, w1);
@@ -1496,21 +1646,25 @@ __device__ bool dogleg_compute_step(Dogleg& S, const double Hs[6], const double 
 
 enum { TERM_MAX_ITER = 0, TERM_GRADIENT = 1, TERM_PARAMETER = 2, TERM_FUNCTION = 3, TERM_MIN_RADIUS = 4, TERM_INVALID = 5 };
 
-// One ceres::Solve (TrustRegionMinimizer, Ceres 1.13/1.14 defaults).  Rejected Gauss-Newton steps that
-// would be recomputed identically (radius still above |GN|) are fast-forwarded: the iteration counter and
-// the radius advance exactly as if the identical candidate had been evaluated and rejected again.
-__device__ int solve_tr(const FitPoints& F, const VbModel& M, int max_iter, int lane, double x[3], double& final_cost,
-                        int& iters_out, int& n_evals) {
-  double xc[3] = {x[0], x[1], x[2]};
-  double x_cost, g[3], H[6];
-  eval_jac(F, M, xc, lane, x_cost, g, H);
-  n_evals++;
-  double scale[3];
-  scale[0] = 1.0 / (1.0 + sqrt(H[0]));
-  scale[1] = 1.0 / (1.0 + sqrt(H[3]));
-  scale[2] = 1.0 / (1.0 + sqrt(H[5]));
-  double xnorm = norm3(xc);
-  double best_cost = x_cost, xbest[3] = {xc[0], xc[1], xc[2]};
+// One ceres::Solve (TrustRegionMinimizer, Ceres 1.13/1.14 defaults) on one warp.  Written as a single loop
+// whose head evaluates the cost at the current candidate (the first candidate is the start point and is always
+// "accepted"), so that the classification / evaluation code exists exactly once in the kernel image.
+// Rejected Gauss-Newton steps that would be recomputed identically (radius still above |GN|) are fast-forwarded:
+// iteration counter and radius advance exactly as if the same candidate had been evaluated and rejected again.
+template <typename IdxT>
+__device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, int oob_i, int max_iter, int lane,
+                                     double* x, double* final_cost, int* iters_out, int* n_evals_io) {
+  const float2* __restrict__ yz = Fp->yz;
+  const uint32_t* __restrict__ wbits = Fp->wbits;
+  IdxT* list = Fp->list;
+  const int n = Fp->n, list_cap = Fp->list_cap;
+  const VbModel M = *Mp;
+  const bool oob = oob_i != 0;
+
+  double xc[3] = {x[0], x[1], x[2]}, cand[3] = {x[0], x[1], x[2]};
+  double g[3] = {0, 0, 0}, H[6] = {0, 0, 0, 0, 0, 0}, scale[3] = {1, 1, 1};
+  double x_cost = 0.0, xnorm = 0.0, best_cost = 0.0, xbest[3] = {x[0], x[1], x[2]};
+  double model_change = 0.0, gmax = 0.0;
   Dogleg S;
   S.radius = 1e4;
   S.mu = 1e-8;
@@ -1518,69 +1672,81 @@ __device__ int solve_tr(const FitPoints& F, const VbModel& M, int max_iter, int 
   S.sub1d = 0;
   S.alpha = 0.0;
   S.step_norm = 0.0;
-  int iter = 0, invalid = 0, term = TERM_MAX_ITER;
-  bool succ = true;
-  double gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
+  int iter = 0, invalid = 0, term = TERM_MAX_ITER, n_evals = 0;
+  bool succ = true, first = true;
   for (;;) {
-    if (iter >= max_iter) { term = TERM_MAX_ITER; break; }
-    if (succ && gmax <= 1e-10) { term = TERM_GRADIENT; break; }
-    if (S.radius <= 1e-32) { term = TERM_MIN_RADIUS; break; }
-    iter++;
-    double Hs[6], gs[3], step[3];
-    Hs[0] = H[0] * scale[0] * scale[0];
-    Hs[1] = H[1] * scale[0] * scale[1];
-    Hs[2] = H[2] * scale[0] * scale[2];
-    Hs[3] = H[3] * scale[1] * scale[1];
-    Hs[4] = H[4] * scale[1] * scale[2];
-    Hs[5] = H[5] * scale[2] * scale[2];
-    for (int i = 0; i < 3; ++i) gs[i] = g[i] * scale[i];
-    const bool ok = dogleg_compute_step(S, Hs, gs, step);
-    bool valid = false;
-    double model_change = 0.0;
-    if (ok) {
-      model_change = -((step[0] * gs[0] + step[1] * gs[1] + step[2] * gs[2]) + 0.5 * quad3(Hs, step, step));
-      valid = model_change > 0.0;
+    // ---- cost at the candidate ----
+    double sn, cs;
+    sincos_once(cand[0], &sn, &cs);
+    double a[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) a[q] = 0.0;
+    int n1 = 0, n2 = 0;
+    for (int k0 = 0; k0 < n; k0 += list_cap) {
+      classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, cand[1], cand[2], lane, k0, min(k0 + list_cap, n), n1, n2);
+      list_pass<IdxT>(yz, wbits, list, list_cap, M, oob, false, cs, sn, cand[1], cand[2], lane, n1, n2, a);
+      if (k0 + list_cap < n) __syncwarp();
     }
-    if (!valid) {
-      if (++invalid >= 5) { term = TERM_INVALID; break; }
-      S.mu *= 10.0;
-      S.reuse = 0;
-      succ = false;
-      continue;
-    }
-    invalid = 0;
-    double cand[3];
-    for (int i = 0; i < 3; ++i) cand[i] = xc[i] + step[i] * scale[i];
-    const double cc = eval_cost(F, M, cand, lane);
+    const double cc = warp_butterfly(a[0]);
     n_evals++;
-    const double d0 = xc[0] - cand[0], d1 = xc[1] - cand[1], d2 = xc[2] - cand[2];
-    const double step_norm = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-    if (step_norm <= 1e-8 * (xnorm + 1e-8)) { term = TERM_PARAMETER; break; }
-    const double cost_change = x_cost - cc;
-    if (fabs(cost_change) <= 1e-6 * x_cost) { term = TERM_FUNCTION; break; }
-    const double quality = cost_change / model_change;
-    if (quality > 1e-3) {
+    bool accept = true;
+    double quality = 1.0;
+    if (!first) {
+      const double d0 = xc[0] - cand[0], d1 = xc[1] - cand[1], d2 = xc[2] - cand[2];
+      const double step_norm = dsqrt(d0 * d0 + d1 * d1 + d2 * d2);
+      if (step_norm <= 1e-8 * (xnorm + 1e-8)) { term = TERM_PARAMETER; break; }
+      const double cost_change = x_cost - cc;
+      if (fabs(cost_change) <= 1e-6 * x_cost) { term = TERM_FUNCTION; break; }
+      quality = ddiv(cost_change, model_change);
+      accept = quality > 1e-3;
+    }
+    if (accept) {
+      // ---- Jacobian at the accepted point: reuse the lists when the frame is a single chunk ----
       for (int i = 0; i < 3; ++i) xc[i] = cand[i];
       xnorm = norm3(xc);
-      eval_jac(F, M, xc, lane, x_cost, g, H);
-      n_evals++;
+      x_cost = cc;
+#pragma unroll
+      for (int q = 0; q < 9; ++q) a[q] = 0.0;
+      if (n <= list_cap) {
+        list_pass<IdxT>(yz, wbits, list, list_cap, M, oob, true, cs, sn, xc[1], xc[2], lane, n1, n2, a);
+      } else {
+        for (int k0 = 0; k0 < n; k0 += list_cap) {
+          __syncwarp();
+          classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, xc[1], xc[2], lane, k0, min(k0 + list_cap, n), n1, n2);
+          list_pass<IdxT>(yz, wbits, list, list_cap, M, oob, true, cs, sn, xc[1], xc[2], lane, n1, n2, a);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 9; ++q) a[q] = warp_butterfly(a[q]);
+      g[0] = a[0];
+      g[1] = a[1];
+      g[2] = a[2];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) H[q] = a[3 + q];
       gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
       succ = true;
-      if (quality < 0.25) S.radius *= 0.5;
-      if (quality > 0.75) S.radius = fmax(S.radius, 3.0 * S.step_norm);
-      S.mu = fmax(1e-8, 2.0 * S.mu / 10.0);
-      S.reuse = 0;
-      if (x_cost < best_cost) {
+      if (first) {
+        scale[0] = ddiv(1.0, 1.0 + dsqrt(H[0]));
+        scale[1] = ddiv(1.0, 1.0 + dsqrt(H[3]));
+        scale[2] = ddiv(1.0, 1.0 + dsqrt(H[5]));
         best_cost = x_cost;
-        for (int i = 0; i < 3; ++i) xbest[i] = xc[i];
+      } else {
+        if (quality < 0.25) S.radius *= 0.5;
+        if (quality > 0.75) S.radius = fmax(S.radius, 3.0 * S.step_norm);
+        S.mu = fmax(1e-8, ddiv(2.0 * S.mu, 10.0));
+        S.reuse = 0;
+        if (x_cost < best_cost) {
+          best_cost = x_cost;
+          for (int i = 0; i < 3; ++i) xbest[i] = xc[i];
+        }
       }
     } else {
       succ = false;
-      const bool was_gn = norm3(S.gn) <= S.radius;
+      const double gnn = norm3(S.gn);
+      const bool was_gn = gnn <= S.radius;
       S.radius *= 0.5;
       S.reuse = 1;
       if (was_gn) {
-        const double gnn = norm3(S.gn);
         // the identical Gauss-Newton candidate would be evaluated and rejected again
         while (iter < max_iter && gnn <= S.radius && S.radius > 1e-32) {
           iter++;
@@ -1588,10 +1754,43 @@ __device__ int solve_tr(const FitPoints& F, const VbModel& M, int max_iter, int 
         }
       }
     }
+    first = false;
+    // ---- next trust-region step (loops over invalid steps) ----
+    bool stop = false;
+    double step[3] = {0, 0, 0};
+    for (;;) {
+      if (iter >= max_iter) { term = TERM_MAX_ITER; stop = true; break; }
+      if (succ && gmax <= 1e-10) { term = TERM_GRADIENT; stop = true; break; }
+      if (S.radius <= 1e-32) { term = TERM_MIN_RADIUS; stop = true; break; }
+      iter++;
+      double Hs[6], gs[3];
+      Hs[0] = H[0] * scale[0] * scale[0];
+      Hs[1] = H[1] * scale[0] * scale[1];
+      Hs[2] = H[2] * scale[0] * scale[2];
+      Hs[3] = H[3] * scale[1] * scale[1];
+      Hs[4] = H[4] * scale[1] * scale[2];
+      Hs[5] = H[5] * scale[2] * scale[2];
+      for (int i = 0; i < 3; ++i) gs[i] = g[i] * scale[i];
+      const bool ok = dogleg_compute_step(S, Hs, gs, step);
+      bool valid = false;
+      if (ok) {
+        model_change = -((step[0] * gs[0] + step[1] * gs[1] + step[2] * gs[2]) + 0.5 * quad3(Hs, step, step));
+        valid = model_change > 0.0;
+      }
+      if (valid) break;
+      if (++invalid >= 5) { term = TERM_INVALID; stop = true; break; }
+      S.mu *= 10.0;
+      S.reuse = 0;
+      succ = false;
+    }
+    if (stop) break;
+    invalid = 0;
+    for (int i = 0; i < 3; ++i) cand[i] = xc[i] + step[i] * scale[i];
   }
   for (int i = 0; i < 3; ++i) x[i] = xbest[i];
-  final_cost = best_cost;
-  iters_out = iter;
+  *final_cost = best_cost;
+  *iters_out = iter;
+  *n_evals_io += n_evals;
   return term;
 }
 
@@ -1607,69 +1806,103 @@ __device__ __forceinline__ void rigid_inverse(const float T[16], float O[16]) {
   O[12] = 0.f; O[13] = 0.f; O[14] = 0.f; O[15] = 1.f;
 }
 
-__global__ void __launch_bounds__(kFitThreads) board_fit_kernel(const Workspace w, const DevParams p) {
+// SMEM = true : frames with at most 65535 optimiser points (16-bit candidate lists + colour bits in shared memory)
+// SMEM = false: larger frames; same code on global-memory scratch.  Both are launched; each skips the other's frames.
+#ifndef FIT_MINB
+#define FIT_MINB 7
+#endif
+template <bool SMEM>
+__global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 4) board_fit_kernel(const Workspace w, const DevParams p) {
+  using IdxT = typename std::conditional<SMEM, uint16_t, uint32_t>::type;
   extern __shared__ unsigned char fit_sm[];
   __shared__ double s_x[2][3];
   __shared__ double s_cost[2];
+  __shared__ float s_ext[2][2];
 
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   ilcc2_diag* d = w.diag + f;
   float* corners = w.corners + (size_t)f * p.ncorners * 3;
   const int st = d->status;
+  const int n = w.opt_count[f];
+  if (st == ILCC2_OK && (n <= 65535) != SMEM) return;  // the other instantiation owns this frame
   if (st != ILCC2_OK) {
-    for (int i = tid; i < p.ncorners * 3; i += kFitThreads) corners[i] = NAN;
-    if (tid == 0) w.status[f] = st;
+    if (SMEM) {
+      for (int i = tid; i < p.ncorners * 3; i += kFitThreads) corners[i] = NAN;
+      if (tid == 0) w.status[f] = st;
+    }
     return;
   }
   const unsigned flags = w.flags ? (unsigned)w.flags[f] : w.default_flags;
-  const int n = w.opt_count[f];
-  FitPoints F;
-  F.n = n;
   const float2* gyz = w.opt_yz + (size_t)f * w.cap;
   const uint8_t* gwh = w.opt_white + (size_t)f * w.cap;
-  if (n <= kFitSmemPts) {
-    float2* syz = reinterpret_cast<float2*>(fit_sm);
-    uint8_t* swh = fit_sm + sizeof(float2) * kFitSmemPts;
-    for (int k = tid; k < n; k += kFitThreads) {
-      syz[k] = gyz[k];
-      swh[k] = gwh[k];
-    }
-    F.yz = syz;
-    F.white = swh;
-  } else {
+  FitPts<IdxT> F;
+  F.n = n;
+  uint32_t* wbits;
+  if (SMEM) {
+    // shared memory holds the two candidate lists (16-bit indices) and the colour bits; the points themselves are
+    // read through L1 (a frame's optimiser points are ~20 KB and 7 frames share an SM), which keeps the CTA's
+    // shared-memory footprint at 13 KB so that registers, not shared memory, bound the residency.
+    IdxT* lists = reinterpret_cast<IdxT*>(fit_sm + sizeof(uint32_t) * (kFitListCap / 32));
+    F.list = lists + (size_t)warp * kFitListCap;
+    F.list_cap = kFitListCap;
     F.yz = gyz;
-    F.white = gwh;
+    wbits = (n <= kFitListCap) ? reinterpret_cast<uint32_t*>(fit_sm) : w.fit_scratch + (size_t)f * w.fit_stride;
+  } else {
+    uint32_t* g = w.fit_scratch + (size_t)f * w.fit_stride;
+    wbits = g;
+    F.yz = gyz;
+    F.list = reinterpret_cast<IdxT*>(g + (w.cap + 31) / 32 + (size_t)warp * w.cap);
+    F.list_cap = w.cap;
   }
+  float ymax = 0.f, zmax = 0.f;
+  for (int base = warp * 32; base < n; base += kFitThreads) {  // stage points; colour flags -> one bit per point
+    const int k = base + lane;
+    const bool v = k < n;
+    const float2 q = v ? gyz[k] : make_float2(0.f, 0.f);
+    ymax = fmaxf(ymax, fabsf(q.x));
+    zmax = fmaxf(zmax, fabsf(q.y));
+    const unsigned m = __ballot_sync(FULL, v && gwh[k] != 0);
+    if (lane == 0) wbits[base >> 5] = m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ymax = fmaxf(ymax, __shfl_xor_sync(FULL, ymax, o));
+    zmax = fmaxf(zmax, __shfl_xor_sync(FULL, zmax, o));
+  }
+  if (lane == 0) {
+    s_ext[warp][0] = ymax;
+    s_ext[warp][1] = zmax;
+  }
+  F.wbits = wbits;
   if (tid < 2) s_cost[tid] = 0.0;
   __syncthreads();
 
   const bool autom = (flags & ILCC2_FLAG_AUTO) != 0;
   VbModel M;
-  M.W = p.W;
-  M.H = p.H;
+  M.Wd = (double)p.W;
+  M.Hd = (double)p.H;
   M.inv_g = p.inv_g;
   M.wg2 = p.wg2;
   M.hg2 = p.hg2;
   M.ha = p.huber_a;
   M.hb = p.huber_b;
+  M.two_ha = 2.0 * p.huber_a;
+  M.ymax_zmax = fmaxf(s_ext[0][0], s_ext[1][0]) + fmaxf(s_ext[0][1], s_ext[1][1]);
   if (autom || warp == 0) {
     const int h_first = autom ? warp : 0;
     const int h_last = autom ? warp : ((flags & ILCC2_FLAG_TOPLEFT_WHITE) ? 1 : 0);
     double x[3] = {0.0, 0.0, 0.0};
     for (int h = h_first; h <= h_last; ++h) {  // manual mode: 'd' warm-starts hypothesis 1 from hypothesis 0
-      int evals = 0;
+      int evals = 0, it0 = 0, it1 = 0;
       double fc = 0.0;
-      for (int phase = 0; phase < 2; ++phase) {
-        M.tlw = h;
-        M.oob = phase == 0 ? 1 : 0;
-        int it = 0;
-        const int term = solve_tr(F, M, p.max_solver_iter, lane, x, fc, it, evals);
-        if (lane == 0) {
-          d->iters[h][phase] = it;
-          d->term[h][phase] = term;
-        }
-      }
+      M.tlw = h;
+      const int term0 = solve_tr<IdxT>(&F, &M, 1, p.max_solver_iter, lane, x, &fc, &it0, &evals);  // useOutofBoard
+      const int term1 = solve_tr<IdxT>(&F, &M, 0, p.max_solver_iter, lane, x, &fc, &it1, &evals);  // then without
       if (lane == 0) {
+        d->iters[h][0] = it0;
+        d->iters[h][1] = it1;
+        d->term[h][0] = term0;
+        d->term[h][1] = term1;
         d->n_evals[h] = evals;
         d->cost[h] = fc;
         for (int i = 0; i < 3; ++i) {
@@ -1713,34 +1946,20 @@ __global__ void __launch_bounds__(kFitThreads) board_fit_kernel(const Workspace 
   }
 }
 
-size_t fit_smem_bytes() { return (sizeof(float2) + 1) * (size_t)kFitSmemPts; }
+size_t fit_smem_bytes() {
+  return sizeof(uint32_t) * (kFitListCap / 32) + 2 * sizeof(uint16_t) * kFitListCap;
+}
 
 void launch_board_fit(const Workspace& w, const DevParams& p, cudaStream_t s) {
-  board_fit_kernel<<<w.n_frames, kFitThreads, fit_smem_bytes(), s>>>(w, p);
+  board_fit_kernel<true><<<w.n_frames, kFitThreads, fit_smem_bytes(), s>>>(w, p);
+  if (w.cap > 65535) board_fit_kernel<false><<<w.n_frames, kFitThreads, 0, s>>>(w, p);
 }
 
 cudaError_t configure_kernels() {
-  // forward half of the 5x5x5 stencil: the 13 offsets of the 3x3x3 core first, then the 49 outer ones
-  signed char off[62][3];
-  int n = 0;
-  for (int pass = 0; pass < 2; ++pass)
-    for (int dz = -2; dz <= 2; ++dz)
-      for (int dy = -2; dy <= 2; ++dy)
-        for (int dx = -2; dx <= 2; ++dx) {
-          const bool fwd = dz > 0 || (dz == 0 && (dy > 0 || (dy == 0 && dx > 0)));
-          if (!fwd) continue;
-          const bool core = dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1;
-          if ((pass == 0) != core) continue;
-          off[n][0] = (signed char)dx;
-          off[n][1] = (signed char)dy;
-          off[n][2] = (signed char)dz;
-          ++n;
-        }
-  cudaError_t e = cudaMemcpyToSymbol(c_fwd_off, off, sizeof(off));
+  cudaError_t e;
+  e = cudaFuncSetAttribute(cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem_bytes());
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem_bytes());
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(board_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem_bytes());
+  e = cudaFuncSetAttribute(board_fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem_bytes());
   return e;
 }
 

@@ -892,12 +892,16 @@ static double eval_cost(vb_problem* Pb, const double x[3]) {
 }
 
 /* cost, g = J^T r, H = J^T J with the Huber corrector applied ([UPSTREAM Ceres] Corrector:
- * rho'' <= 0 for Huber, so residual and Jacobian row are both scaled by sqrt(rho')). */
+ * rho'' <= 0 for Huber, so residual and Jacobian row are both scaled by sqrt(rho')).
+ * Canonical summation order: the cost is summed like eval_cost (point k -> partial k mod 32); the gradient and
+ * J^T J terms only exist for points with a non-zero residual, and the j-th such point (in k order) goes to
+ * partial j mod 32 -- the order in which a warp walks the compacted list of non-zero residuals. */
 static void eval_jac(vb_problem* Pb, const double x[3], double* cost, double g[3], double H[6]) {
   const vb_model* M = Pb->M;
   const double c = cos(x[0]), s = sin(x[0]);
   racc a[10];
   for (int q = 0; q < 10; ++q) racc_zero_w(&a[q], RW_WARP);
+  int j = 0;
   for (int k = 0; k < Pb->n; ++k) {
     double si, sj;
     const double y = Pb->yz[2 * k], z = Pb->yz[2 * k + 1];
@@ -919,15 +923,16 @@ static void eval_jac(vb_problem* Pb, const double x[3], double* cost, double g[3
       rr = sc * r;
     }
     racc_add(&a[0], k, huber_cost(M, r));
-    racc_add(&a[1], k, j0 * rr);
-    racc_add(&a[2], k, j1 * rr);
-    racc_add(&a[3], k, j2 * rr);
-    racc_add(&a[4], k, j0 * j0);
-    racc_add(&a[5], k, j0 * j1);
-    racc_add(&a[6], k, j0 * j2);
-    racc_add(&a[7], k, j1 * j1);
-    racc_add(&a[8], k, j1 * j2);
-    racc_add(&a[9], k, j2 * j2);
+    racc_add(&a[1], j, j0 * rr);
+    racc_add(&a[2], j, j1 * rr);
+    racc_add(&a[3], j, j2 * rr);
+    racc_add(&a[4], j, j0 * j0);
+    racc_add(&a[5], j, j0 * j1);
+    racc_add(&a[6], j, j0 * j2);
+    racc_add(&a[7], j, j1 * j1);
+    racc_add(&a[8], j, j1 * j2);
+    racc_add(&a[9], j, j2 * j2);
+    ++j;
   }
   *cost = racc_total(&a[0]);
   for (int q = 0; q < 3; ++q) g[q] = racc_total(&a[1 + q]);
