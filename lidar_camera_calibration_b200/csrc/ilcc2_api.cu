@@ -243,8 +243,10 @@ int ilcc2_create(const ilcc2_params* params, int device, int max_frames, int max
   A(dev_alloc(h, &w.opt_yz, F * R));
   A(dev_alloc(h, &w.opt_white, F * R));
   A(dev_alloc(h, &w.opt_count, F));
+  A(dev_alloc(h, &w.fit_order, F));
+  w.num_sms = prop.multiProcessorCount;
   w.fit_stride = (h->cap + 31) / 32 + 2ll * h->cap;
-  A(dev_alloc(h, &w.fit_scratch, h->cap > kFitListCap ? F * (size_t)w.fit_stride : 1));
+  A(dev_alloc(h, &w.fit_scratch, h->cap > kFitBitsCap ? F * (size_t)w.fit_stride : 1));
   A(dev_alloc(h, &h->d_clicks, F * 3));
   A(dev_alloc(h, &h->d_flags, F));
   A(dev_alloc(h, &h->d_pdelta, F));
@@ -400,7 +402,7 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
   launch_board_fit(w, h->dp, s);
   CU_TRY(h, stage_done(5));
   h->ev_valid = prof;
-  h->launches += kStages + (h->cap > 65535 ? 1 : 0) + (h->cap > kClusterSmemPts ? 1 : 0);
+  h->launches += kStages + 1 + (h->cap > kFitBitsCap ? 1 : 0) + (h->cap > kClusterSmemPts ? 1 : 0);
   CU_TRY(h, cudaGetLastError());
 
   h->last_n_frames = n_frames;

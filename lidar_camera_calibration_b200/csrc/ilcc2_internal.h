@@ -33,10 +33,12 @@ constexpr int kRoiUnroll = 4;         // K1 records per thread per tile
 constexpr int kClusterThreads = 256;  // K2 CTA size
 constexpr int kClusterSmemPts = 4096; // K2: frames with at most this many ROI points cluster in shared memory
 constexpr int kClusterSmemSlots = 8192;
-constexpr int kClusterBitmapRows = 3072; // K2: occupancy bitmap rows (ncy*ncz) that fit the shared-memory layout
+constexpr int kClusterBitmapRows = 2944; // K2: occupancy bitmap rows (ncy*ncz) that fit the shared-memory layout
+constexpr int kClusterQueue = 160;       // K2: per-warp queue of (cell, neighbour) pairs: 32 lanes x 5 dx
 constexpr int kPlaneThreads = 128;    // K3/K4 CTA size == canonical reduction width of their double sums
 constexpr int kFitThreads = 64;       // K5: warp 0 = hypothesis topleftWhite=false, warp 1 = true
 constexpr int kFitListCap = 3200;     // K5: per-warp candidate list buffer in shared memory = chunk length (multiple of 32)
+constexpr int kFitBitsCap = 8192;      // K5: colour bits kept in shared memory; larger frames take the global-memory path
 constexpr int kRndTable = 8192;       // PCL RANSAC draw table length
 
 // Everything a launch needs; passed by value.
@@ -68,6 +70,8 @@ struct Workspace {
   float2* opt_yz;              // [F][R] non-gray board points in the PCA frame (y', z')
   uint8_t* opt_white;          // [F][R]
   int* opt_count;              // [F]
+  int* fit_order;              // [F] block index -> frame for K5 (work-balanced order)
+  int num_sms;
   uint32_t* fit_scratch;       // [F][fit_stride] K5 global-memory path: colour bits + two index lists
   long long fit_stride;
   const uint32_t* rnd_table;   // [kRndTable] PCL RANSAC draws

@@ -337,6 +337,8 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
   extern __shared__ int sm[];
   __shared__ int s_warp[NT / 32];
   __shared__ int s_nocc, s_nkept, s_chosen_root;
+  __shared__ unsigned s_queue_fallback[SMEM ? 1 : (NT / 32) * kClusterQueue];  // code words
+  __shared__ int s_queue_slot[SMEM ? 1 : (NT / 32) * kClusterQueue];         // slot ids (do not fit 13 bits)
 
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   ilcc2_diag* d = w.diag + f;
@@ -351,6 +353,8 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
   int *key, *head, *parent;
   NxtT *nxt, *occ;
   unsigned* bitmap = nullptr;
+  unsigned* queue = nullptr;  // per-warp queue of (cell, neighbour) pairs
+  int* qslot = nullptr;
   const int nrows = p.ncy * p.ncz;
   const bool use_bitmap = SMEM && p.ncx <= 32 && nrows <= kClusterBitmapRows;
   if (SMEM) {
@@ -361,6 +365,7 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
     nxt = reinterpret_cast<NxtT*>(parent + kClusterSmemPts);
     occ = nxt + kClusterSmemPts;
     bitmap = reinterpret_cast<unsigned*>(occ + kClusterSmemPts);
+    queue = bitmap + kClusterBitmapRows + warp * kClusterQueue;
   } else {
     TS = w.cl_ts;
     int* g = w.cl_scratch + (size_t)f * w.cl_stride;
@@ -369,6 +374,8 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
     parent = head + TS;
     nxt = reinterpret_cast<NxtT*>(parent + w.cap);
     occ = nxt + w.cap;
+    queue = s_queue_fallback + warp * kClusterQueue;
+    qslot = s_queue_slot + warp * kClusterQueue;
   }
   for (int i = tid; i < TS; i += NT) {
     key[i] = -1;
@@ -427,34 +434,63 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
       dy = c_row_dy[r];
       dz = c_row_dz[r];
     }
-    for (int c0 = 0; c0 < nocc; c0 += cells_per_iter) {
+    for (int c0 = 0; c0 < nocc; c0 += cells_per_iter) {  // warp-uniform trip count
       const int ci = c0 + tid / G;
-      if (ci >= nocc || gl >= nrow) continue;
-      const int a = (int)occ[ci];
-      const int ka = key[a];
-      const int ax = ka & 1023, ay = (ka >> 10) & 1023, az = ka >> 20;
-      const int by = ay + dy, bz = az + dz;
-      if ((unsigned)by >= (unsigned)p.ncy || (unsigned)bz >= (unsigned)p.ncz) continue;
-      // candidate dx set of this row for this pass, as a 5-bit mask (bit dx+2)
-      const bool own = dy == 0 && dz == 0;
-      const bool core_row = dy >= -1 && dy <= 1 && dz <= 1;
-      unsigned want;
-      if (pass == 0)
-        want = own ? 0x08u : 0x0eu;                               // dx = 1 | dx in {-1,0,1}
-      else
-        want = own ? 0x10u : (core_row ? 0x11u : 0x1fu);          // dx = 2 | dx = +-2 | all five
-      if (use_bitmap) {
-        const unsigned row = bitmap[bz * p.ncy + by];
-        const unsigned win = (unsigned)((((unsigned long long)row) << 2) >> ax) & 0x1fu;  // bits ax-2 .. ax+2
-        want &= win;
+      // (a) each lane finds the occupied neighbour cells of its (cell, row): a 5-bit mask over dx
+      unsigned want = 0u;
+      int a = 0;
+      if (ci < nocc && gl < nrow) {
+        a = (int)occ[ci];
+        const int ka = key[a];
+        const int ax = ka & 1023, ay = (ka >> 10) & 1023, az = ka >> 20;
+        const int by = ay + dy, bz = az + dz;
+        if ((unsigned)by < (unsigned)p.ncy && (unsigned)bz < (unsigned)p.ncz) {
+          const bool own = dy == 0 && dz == 0;
+          const bool core_row = dy >= -1 && dy <= 1 && dz <= 1;
+          if (pass == 0)
+            want = own ? 0x08u : 0x0eu;                       // dx = 1 | dx in {-1,0,1}
+          else
+            want = own ? 0x10u : (core_row ? 0x11u : 0x1fu);  // dx = 2 | dx = +-2 | all five
+          // drop dx that fall outside the grid (bit j <-> bx = ax + j - 2)
+          if (ax < 2) want &= (0x1fu << (2 - ax)) & 0x1fu;
+          if (ax + 2 >= p.ncx) want &= 0x1fu >> (ax + 3 - p.ncx);
+          if (use_bitmap) {
+            const unsigned row = bitmap[bz * p.ncy + by];
+            want &= (unsigned)((((unsigned long long)row) << 2) >> ax) & 0x1fu;  // bits ax-2 .. ax+2
+          }
+        }
       }
+      // (b) compact the (cell, neighbour) pairs of the warp into its queue: all lanes then work on real pairs
+      const int cnt = __popc(want);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int total = __shfl_sync(FULL, incl, 31);
+      int off = incl - cnt;
+      const int rcode = pass == 0 ? (gl == 0 ? 0 : gl == 1 ? 1 : gl + 2) : gl;
       while (want) {
         const int bit = __ffs(want) - 1;
         want &= want - 1;
-        const int bx = ax + bit - 2;
-        if ((unsigned)bx >= (unsigned)p.ncx) continue;
-        join_cells<NxtT>(P, key, head, nxt, parent, mask, a, pack_cell(bx, by, bz), tol2);
+        if (SMEM) {
+          queue[off++] = (unsigned)a | ((unsigned)bit << 13) | ((unsigned)rcode << 16);
+        } else {
+          qslot[off] = a;
+          queue[off++] = ((unsigned)bit << 13) | ((unsigned)rcode << 16);
+        }
       }
+      __syncwarp();
+      for (int e = lane; e < total; e += 32) {
+        const unsigned q = queue[e];
+        const int qa = SMEM ? (int)(q & 8191u) : qslot[e];
+        const int bit = (int)((q >> 13) & 7u), r = (int)(q >> 16);
+        const int ka = key[qa];
+        const int bx = (ka & 1023) + bit - 2, by = ((ka >> 10) & 1023) + c_row_dy[r], bz = (ka >> 20) + c_row_dz[r];
+        join_cells<NxtT>(P, key, head, nxt, parent, mask, qa, pack_cell(bx, by, bz), tol2);
+      }
+      __syncwarp();
     }
     __syncthreads();
   }
@@ -539,7 +575,7 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
 
 size_t cluster_smem_bytes() {
   return sizeof(int) * (2 * kClusterSmemSlots + kClusterSmemPts) + sizeof(uint16_t) * 2 * kClusterSmemPts +
-         sizeof(unsigned) * kClusterBitmapRows;
+         sizeof(unsigned) * (kClusterBitmapRows + (kClusterThreads / 32) * kClusterQueue);
 }
 
 void launch_cluster(const Workspace& w, const DevParams& p, cudaStream_t s) {
@@ -1655,9 +1691,18 @@ template <typename IdxT>
 __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, int oob_i, int max_iter, int lane,
                                      double* x, double* final_cost, int* iters_out, int* n_evals_io) {
   const float2* __restrict__ yz = Fp->yz;
-  const uint32_t* __restrict__ wbits = Fp->wbits;
+  const uint32_t* wbits = Fp->wbits;
   IdxT* list = Fp->list;
-  const int n = Fp->n, list_cap = Fp->list_cap;
+  int list_cap = Fp->list_cap;
+  if (std::is_same<IdxT, uint16_t>::value) {
+    // shared-memory instantiation: derive the pointers from the shared array itself so that the compiler emits
+    // LDS/STS with 32-bit addresses instead of generic loads/stores
+    extern __shared__ unsigned char fit_sm[];
+    wbits = reinterpret_cast<const uint32_t*>(fit_sm);
+    list = reinterpret_cast<IdxT*>(fit_sm + sizeof(uint32_t) * (kFitBitsCap / 32)) + (size_t)(threadIdx.x >> 5) * kFitListCap;
+    list_cap = kFitListCap;
+  }
+  const int n = Fp->n;
   const VbModel M = *Mp;
   const bool oob = oob_i != 0;
 
@@ -1806,7 +1851,48 @@ __device__ __forceinline__ void rigid_inverse(const float T[16], float O[16]) {
   O[12] = 0.f; O[13] = 0.f; O[14] = 0.f; O[15] = 1.f;
 }
 
-// SMEM = true : frames with at most 65535 optimiser points (16-bit candidate lists + colour bits in shared memory)
+// Work-balancing permutation for K5: frames bucketed by their number of optimiser points (the work of a solve is
+// ~ points x evaluations), largest first, and dealt to thread blocks in snake order over rounds of `num_sms`
+// blocks, so that the frames resident on one SM add up to about the same work.  One CTA; any number of frames.
+__global__ void __launch_bounds__(1024) fit_order_kernel(const Workspace w, int num_sms) {
+  constexpr int NB = 128;
+  __shared__ int s_hist[NB], s_start[NB];
+  const int tid = threadIdx.x, F = w.n_frames;
+  for (int i = tid; i < NB; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  auto bucket = [&](int f) {
+    const int n = (w.diag[f].status == ILCC2_OK) ? w.opt_count[f] : 0;
+    return NB - 1 - min(n >> 5, NB - 1);  // descending size
+  };
+  for (int f = tid; f < F; f += blockDim.x) atomicAdd(&s_hist[bucket(f)], 1);
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int b = 0; b < NB; ++b) {
+      s_start[b] = acc;
+      acc += s_hist[b];
+    }
+  }
+  __syncthreads();
+  const int full = (F / num_sms) * num_sms;
+  for (int f = tid; f < F; f += blockDim.x) {
+    const int pos = atomicAdd(&s_start[bucket(f)], 1);
+    int blk = pos;
+    if (pos < full) {
+      const int round = pos / num_sms, j = pos % num_sms;
+      blk = round * num_sms + ((round & 1) ? num_sms - 1 - j : j);
+    }
+#ifdef FIT_ORDER_IDENTITY
+    blk = f;
+#elif defined(FIT_ORDER_SORTED)
+    blk = pos;
+#endif
+    w.fit_order[blk] = f;
+  }
+}
+
+// SMEM = true : frames with at most kFitBitsCap optimiser points (16-bit candidate lists + colour bits in shared memory;
+//               frames above kFitListCap points are evaluated in chunks of kFitListCap)
 // SMEM = false: larger frames; same code on global-memory scratch.  Both are launched; each skips the other's frames.
 #ifndef FIT_MINB
 #define FIT_MINB 7
@@ -1819,12 +1905,13 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 4) board_fit_ke
   __shared__ double s_cost[2];
   __shared__ float s_ext[2][2];
 
-  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int f = w.fit_order[blockIdx.x];  // big frames first, dealt to the SMs in snake order (fit_order_kernel)
   ilcc2_diag* d = w.diag + f;
   float* corners = w.corners + (size_t)f * p.ncorners * 3;
   const int st = d->status;
   const int n = w.opt_count[f];
-  if (st == ILCC2_OK && (n <= 65535) != SMEM) return;  // the other instantiation owns this frame
+  if (st == ILCC2_OK && (n <= kFitBitsCap) != SMEM) return;  // the other instantiation owns this frame
   if (st != ILCC2_OK) {
     if (SMEM) {
       for (int i = tid; i < p.ncorners * 3; i += kFitThreads) corners[i] = NAN;
@@ -1842,11 +1929,11 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 4) board_fit_ke
     // shared memory holds the two candidate lists (16-bit indices) and the colour bits; the points themselves are
     // read through L1 (a frame's optimiser points are ~20 KB and 7 frames share an SM), which keeps the CTA's
     // shared-memory footprint at 13 KB so that registers, not shared memory, bound the residency.
-    IdxT* lists = reinterpret_cast<IdxT*>(fit_sm + sizeof(uint32_t) * (kFitListCap / 32));
+    IdxT* lists = reinterpret_cast<IdxT*>(fit_sm + sizeof(uint32_t) * (kFitBitsCap / 32));
     F.list = lists + (size_t)warp * kFitListCap;
     F.list_cap = kFitListCap;
     F.yz = gyz;
-    wbits = (n <= kFitListCap) ? reinterpret_cast<uint32_t*>(fit_sm) : w.fit_scratch + (size_t)f * w.fit_stride;
+    wbits = reinterpret_cast<uint32_t*>(fit_sm);
   } else {
     uint32_t* g = w.fit_scratch + (size_t)f * w.fit_stride;
     wbits = g;
@@ -1947,12 +2034,13 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 4) board_fit_ke
 }
 
 size_t fit_smem_bytes() {
-  return sizeof(uint32_t) * (kFitListCap / 32) + 2 * sizeof(uint16_t) * kFitListCap;
+  return sizeof(uint32_t) * (kFitBitsCap / 32) + 2 * sizeof(uint16_t) * kFitListCap;
 }
 
 void launch_board_fit(const Workspace& w, const DevParams& p, cudaStream_t s) {
+  fit_order_kernel<<<1, 1024, 0, s>>>(w, w.num_sms);
   board_fit_kernel<true><<<w.n_frames, kFitThreads, fit_smem_bytes(), s>>>(w, p);
-  if (w.cap > 65535) board_fit_kernel<false><<<w.n_frames, kFitThreads, 0, s>>>(w, p);
+  if (w.cap > kFitBitsCap) board_fit_kernel<false><<<w.n_frames, kFitThreads, 0, s>>>(w, p);
 }
 
 cudaError_t configure_kernels() {
