@@ -56,6 +56,12 @@ struct ilcc2_handle {
   // profiling
   bool profiling = false;
   cudaEvent_t ev[kStages + 1] = {};
+  // host-buffer calls: chunked H2D on a private copy stream overlapped with the kernels of the previous chunk
+  cudaStream_t copy_stream = nullptr;
+  static constexpr int kMaxChunks = 64;
+  cudaEvent_t ev_copied[kMaxChunks] = {};
+  cudaEvent_t ev_start = nullptr;
+  int e2e_chunk_frames = 512;
   bool ev_valid = false;
   int64_t launches = 0;
   std::string error;
@@ -264,6 +270,11 @@ int ilcc2_create(const ilcc2_params* params, int device, int max_frames, int max
   }
   if (ce == cudaSuccess) A(configure_kernels());
   for (int i = 0; i <= kStages && ce == cudaSuccess; ++i) A(cudaEventCreate(&h->ev[i]));
+  if (ce == cudaSuccess) A(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < ilcc2_handle::kMaxChunks && ce == cudaSuccess; ++i)
+    A(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+  if (ce == cudaSuccess) A(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+  if (const char* e = getenv("ILCC2_E2E_CHUNK")) h->e2e_chunk_frames = atoi(e) > 0 ? atoi(e) : h->e2e_chunk_frames;
   if (ce != cudaSuccess) {
     const int rc = fail(nullptr, ILCC2_ERR_CUDA, "ilcc2_create: %s", cudaGetErrorString(ce));
     for (void* q : h->allocs) cudaFree(q);
@@ -284,6 +295,10 @@ int ilcc2_destroy(ilcc2_handle* h) {
   if (h->d_points_stage) cudaFree(h->d_points_stage);
   for (int i = 0; i <= kStages; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < ilcc2_handle::kMaxChunks; ++i)
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
   return ILCC2_SUCCESS;
 }
@@ -338,7 +353,6 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
       CU_TRY(h, cudaMalloc(&h->d_points_stage, want > bytes ? want : bytes));
       h->points_stage_bytes = want > bytes ? want : bytes;
     }
-    CU_TRY(h, cudaMemcpyAsync(h->d_points_stage, points, bytes, cudaMemcpyHostToDevice, s));
     CU_TRY(h, cudaMemcpyAsync(h->d_clicks, click_xyz, sizeof(float) * 3 * n_frames, cudaMemcpyHostToDevice, s));
     if (flags) CU_TRY(h, cudaMemcpyAsync(h->d_flags, flags, n_frames, cudaMemcpyHostToDevice, s));
     if (plane_index_delta) CU_TRY(h, cudaMemcpyAsync(h->d_pdelta, plane_index_delta, n_frames, cudaMemcpyHostToDevice, s));
@@ -372,6 +386,7 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
   w.oi = off_intensity;
   w.default_flags = default_flags;
   w.n_frames = n_frames;
+  w.frame_base = 0;
   w.diag = h->d_diag;
   CU_TRY(h, cudaMemsetAsync(h->d_diag, 0, sizeof(ilcc2_diag) * n_frames, s));
 
@@ -390,19 +405,49 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
     }
     return cudaSuccess;
   };
+  // Host buffers: the batch is cut into chunks of frames; chunk c+1 is copied on the copy stream while the five
+  // kernels of chunk c run on the caller's stream (needs page-locked host memory to actually overlap).
+  // Device buffers, profiling runs and ragged batches: one chunk.
+  int chunk = n_frames;
+  if (mem_kind == ILCC2_MEM_HOST && !prof && !frame_offsets && n_frames > h->e2e_chunk_frames) {
+    chunk = h->e2e_chunk_frames;
+    while ((n_frames + chunk - 1) / chunk > ilcc2_handle::kMaxChunks) chunk *= 2;
+  }
+  const int n_chunks = (n_frames + chunk - 1) / chunk;
+  if (mem_kind == ILCC2_MEM_HOST) {
+    if (n_chunks == 1) {
+      CU_TRY(h, cudaMemcpyAsync(h->d_points_stage, points, bytes, cudaMemcpyHostToDevice, s));
+    } else {
+      CU_TRY(h, cudaEventRecord(h->ev_start, s));
+      CU_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_start, 0));
+      const size_t frame_bytes = (size_t)points_per_frame * point_step;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int f0 = c * chunk, nf = (f0 + chunk <= n_frames) ? chunk : n_frames - f0;
+        CU_TRY(h, cudaMemcpyAsync(h->d_points_stage + (size_t)f0 * frame_bytes,
+                                  static_cast<const unsigned char*>(points) + (size_t)f0 * frame_bytes,
+                                  (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CU_TRY(h, cudaEventRecord(h->ev_copied[c], h->copy_stream));
+      }
+    }
+  }
   CU_TRY(h, stage_done(0));
-  launch_roi_filter(w, h->dp, s);
-  CU_TRY(h, stage_done(1));
-  launch_cluster(w, h->dp, s);
-  CU_TRY(h, stage_done(2));
-  launch_plane(w, h->dp, s);
-  CU_TRY(h, stage_done(3));
-  launch_pca_gray(w, h->dp, s);
-  CU_TRY(h, stage_done(4));
-  launch_board_fit(w, h->dp, s);
-  CU_TRY(h, stage_done(5));
+  for (int c = 0; c < n_chunks; ++c) {
+    w.frame_base = c * chunk;
+    w.n_frames = (w.frame_base + chunk <= n_frames) ? chunk : n_frames - w.frame_base;
+    if (n_chunks > 1) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_copied[c], 0));
+    launch_roi_filter(w, h->dp, s);
+    if (n_chunks == 1) CU_TRY(h, stage_done(1));
+    launch_cluster(w, h->dp, s);
+    if (n_chunks == 1) CU_TRY(h, stage_done(2));
+    launch_plane(w, h->dp, s);
+    if (n_chunks == 1) CU_TRY(h, stage_done(3));
+    launch_pca_gray(w, h->dp, s);
+    if (n_chunks == 1) CU_TRY(h, stage_done(4));
+    launch_board_fit(w, h->dp, s);
+    if (n_chunks == 1) CU_TRY(h, stage_done(5));
+    h->launches += kStages + 1 + (h->cap > kFitBitsCap ? 1 : 0) + (h->cap > kClusterSmemPts ? 1 : 0);
+  }
   h->ev_valid = prof;
-  h->launches += kStages + 1 + (h->cap > kFitBitsCap ? 1 : 0) + (h->cap > kClusterSmemPts ? 1 : 0);
   CU_TRY(h, cudaGetLastError());
 
   h->last_n_frames = n_frames;

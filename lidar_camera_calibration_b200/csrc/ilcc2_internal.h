@@ -52,7 +52,8 @@ struct Workspace {
   const uint8_t* flags;        // nullable
   uint32_t default_flags;
   const int8_t* pdelta;        // nullable
-  int n_frames;
+  int n_frames;                // frames in THIS launch (a chunk of the call's batch)
+  int frame_base;              // first frame of the chunk; kernels process frames frame_base + blockIdx.x
   int cap;                     // per-frame capacity R of the ROI-sized arrays
   // scratch
   float4* roi_pts;             // [F][R] ROI points (x,y,z,intensity), input order

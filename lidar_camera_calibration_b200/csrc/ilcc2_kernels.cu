@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kRoiThreads) roi_filter_kernel(const Workspace
   __shared__ int s_tile_total;
   __shared__ unsigned long long s_key[NW];
 
-  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int f = blockIdx.x + w.frame_base, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   long long start;
   int n;
   if (w.frame_off) {
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
   __shared__ unsigned s_queue_fallback[SMEM ? 1 : (NT / 32) * kClusterQueue];  // code words
   __shared__ int s_queue_slot[SMEM ? 1 : (NT / 32) * kClusterQueue];         // slot ids (do not fit 13 bits)
 
-  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int f = blockIdx.x + w.frame_base, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   ilcc2_diag* d = w.diag + f;
   int* sel = w.sel_idx + (size_t)f * w.cap;
   const int M = w.roi_count[f];
@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(kPlaneThreads) plane_kernel(const Workspace w,
   __shared__ double s_part[9 * 128];
   __shared__ double s_out[9];
 
-  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int f = blockIdx.x + w.frame_base, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   ilcc2_diag* d = w.diag + f;
   if (d->status != ILCC2_OK) {
     if (tid == 0) w.brd_count[f] = 0;
@@ -1044,7 +1044,7 @@ __global__ void __launch_bounds__(kPlaneThreads) pca_gray_kernel(const Workspace
   __shared__ int s_status;
   __shared__ int s_warp[NT / 32];
 
-  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int f = blockIdx.x + w.frame_base, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   ilcc2_diag* d = w.diag + f;
   if (d->status != ILCC2_OK) {
     if (tid == 0) w.opt_count[f] = 0;
@@ -1264,6 +1264,7 @@ struct FitPts {
   const float2* yz;
   const uint32_t* wbits;
   int n;
+  float* timing; // debug builds (FIT_TIMING): kilo-cycles spent in evaluation / scalar solver
   IdxT* list;    // this warp's list buffer: L1 grows up from 0, L2 grows down from list_cap-1
   int list_cap;  // entries; also the chunk length (a chunk of list_cap points can never overflow it)
 };
@@ -1360,35 +1361,43 @@ __device__ __forceinline__ void classify_pass(const float2* __restrict__ yz, con
   int c1 = 0, c2 = 0;
   const unsigned lt = (1u << lane) - 1u;
 #ifndef CLS_UNROLL
-#define CLS_UNROLL 1
+#define CLS_UNROLL 4
 #endif
-  constexpr int kClsUnroll = CLS_UNROLL;
-#pragma unroll kClsUnroll
-  for (int base = k0; base < k1; base += 32) {
-    const int k = base + lane;
-    const bool valid = k < k1;
-    const float2 q = __ldg(yz + (valid ? k : k0));
-    const unsigned wword = wbits[base >> 5];
-    const float fi = fmaf(q.x, cg, fmaf(-q.y, sg, tyw));
-    const float fj = fmaf(q.y, cg, fmaf(q.x, sg, tzh));
-    const float ti = fi + kMagicF, tj = fj + kMagicF;
-    const float di = fi - (ti - kMagicF), dj = fj - (tj - kMagicF);  // signed distance to the nearest integer
-    // cell parity: parity(rint) ^ (d < 0)
-    const unsigned par = (__float_as_uint(ti) ^ __float_as_uint(tj) ^ ((__float_as_uint(di) ^ __float_as_uint(dj)) >> 31)) & 1u;
-    const bool interior = fminf(fabsf(di), fabsf(dj)) >= m;
-    const float edge = fmaxf(fabsf(fi - Wh) - Wh, fabsf(fj - Hh) - Hh);  // < 0 inside the board, > 0 outside
-    const bool certain_in = interior && edge <= -m;
-    const bool outb = edge >= m;
-    const bool mism = ((((wword >> lane) ^ tlw ^ par) & 1u) != 0u);
-    const bool is1 = valid && (certain_in ? mism : !outb);
-    const unsigned b1 = __ballot_sync(FULL, is1);
-    if (is1) list[c1 + __popc(b1 & lt)] = (IdxT)k;
-    c1 += __popc(b1);
-    if (oob) {
-      const bool is2 = valid && outb;
-      const unsigned b2 = __ballot_sync(FULL, is2);
-      if (is2) list[list_cap - 1 - (c2 + __popc(b2 & lt))] = (IdxT)k;
-      c2 += __popc(b2);
+  constexpr int U = CLS_UNROLL;  // independent points per lane per iteration: the warp is latency-bound, not issue-bound
+  for (int base = k0; base < k1; base += 32 * U) {
+    bool is1[U], is2[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = base + 32 * u + lane;
+      const bool valid = k < k1;
+      const float2 q = __ldg(yz + (valid ? k : k0));
+      const unsigned wword = wbits[min(base + 32 * u, k1 - 1) >> 5];
+      const float fi = fmaf(q.x, cg, fmaf(-q.y, sg, tyw));
+      const float fj = fmaf(q.y, cg, fmaf(q.x, sg, tzh));
+      const float ti = fi + kMagicF, tj = fj + kMagicF;
+      const float di = fi - (ti - kMagicF), dj = fj - (tj - kMagicF);  // signed distance to the nearest integer
+      // cell parity: parity(rint) ^ (d < 0)
+      const unsigned par =
+          (__float_as_uint(ti) ^ __float_as_uint(tj) ^ ((__float_as_uint(di) ^ __float_as_uint(dj)) >> 31)) & 1u;
+      const bool interior = fminf(fabsf(di), fabsf(dj)) >= m;
+      const float edge = fmaxf(fabsf(fi - Wh) - Wh, fabsf(fj - Hh) - Hh);  // < 0 inside the board, > 0 outside
+      const bool certain_in = interior && edge <= -m;
+      const bool outb = edge >= m;
+      const bool mism = ((((wword >> lane) ^ tlw ^ par) & 1u) != 0u);
+      is1[u] = valid && (certain_in ? mism : !outb);
+      is2[u] = valid && outb;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = base + 32 * u + lane;
+      const unsigned b1 = __ballot_sync(FULL, is1[u]);
+      if (is1[u]) list[c1 + __popc(b1 & lt)] = (IdxT)k;
+      c1 += __popc(b1);
+      if (oob) {
+        const unsigned b2 = __ballot_sync(FULL, is2[u]);
+        if (is2[u]) list[list_cap - 1 - (c2 + __popc(b2 & lt))] = (IdxT)k;
+        c2 += __popc(b2);
+      }
     }
   }
   __syncwarp();
@@ -1719,7 +1728,13 @@ __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, 
   S.step_norm = 0.0;
   int iter = 0, invalid = 0, term = TERM_MAX_ITER, n_evals = 0;
   bool succ = true, first = true;
+#ifdef FIT_TIMING
+  long long t_eval = 0, t_scalar = 0, t_cls = 0, t_jac = 0, t0 = clock64();
+#endif
   for (;;) {
+#ifdef FIT_TIMING
+    { const long long t1 = clock64(); t_scalar += t1 - t0; t0 = t1; }
+#endif
     // ---- cost at the candidate ----
     double sn, cs;
     sincos_once(cand[0], &sn, &cs);
@@ -1728,12 +1743,21 @@ __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, 
     for (int q = 0; q < 9; ++q) a[q] = 0.0;
     int n1 = 0, n2 = 0;
     for (int k0 = 0; k0 < n; k0 += list_cap) {
+#ifdef FIT_TIMING
+      const long long tc0 = clock64();
+#endif
       classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, cand[1], cand[2], lane, k0, min(k0 + list_cap, n), n1, n2);
+#ifdef FIT_TIMING
+      t_cls += clock64() - tc0;
+#endif
       list_pass<IdxT>(yz, wbits, list, list_cap, M, oob, false, cs, sn, cand[1], cand[2], lane, n1, n2, a);
       if (k0 + list_cap < n) __syncwarp();
     }
     const double cc = warp_butterfly(a[0]);
     n_evals++;
+#ifdef FIT_TIMING
+    { const long long t1 = clock64(); t_eval += t1 - t0; t0 = t1; }
+#endif
     bool accept = true;
     double quality = 1.0;
     if (!first) {
@@ -1770,6 +1794,9 @@ __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, 
       for (int q = 0; q < 6; ++q) H[q] = a[3 + q];
       gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
       succ = true;
+#ifdef FIT_TIMING
+      { const long long t1 = clock64(); t_jac += t1 - t0; t0 = t1; }
+#endif
       if (first) {
         scale[0] = ddiv(1.0, 1.0 + dsqrt(H[0]));
         scale[1] = ddiv(1.0, 1.0 + dsqrt(H[3]));
@@ -1836,6 +1863,17 @@ __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, 
   *final_cost = best_cost;
   *iters_out = iter;
   *n_evals_io += n_evals;
+#ifdef FIT_TIMING
+  t_scalar += clock64() - t0;
+  if (lane == 0) {
+    if ((threadIdx.x >> 5) == 0) {
+      atomicAdd(&Fp->timing[0], (float)t_cls * 1e-3f);
+      atomicAdd(&Fp->timing[1], (float)(t_eval - t_cls) * 1e-3f);
+      atomicAdd(&Fp->timing[2], (float)t_jac * 1e-3f);
+      atomicAdd(&Fp->timing[3], (float)t_scalar * 1e-3f);
+    }
+  }
+#endif
   return term;
 }
 
@@ -1860,7 +1898,9 @@ __global__ void __launch_bounds__(1024) fit_order_kernel(const Workspace w, int 
   const int tid = threadIdx.x, F = w.n_frames;
   for (int i = tid; i < NB; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
-  auto bucket = [&](int f) {
+  const int base = w.frame_base;
+  auto bucket = [&](int fl) {
+    const int f = base + fl;
     const int n = (w.diag[f].status == ILCC2_OK) ? w.opt_count[f] : 0;
     return NB - 1 - min(n >> 5, NB - 1);  // descending size
   };
@@ -1887,7 +1927,7 @@ __global__ void __launch_bounds__(1024) fit_order_kernel(const Workspace w, int 
 #elif defined(FIT_ORDER_SORTED)
     blk = pos;
 #endif
-    w.fit_order[blk] = f;
+    w.fit_order[base + blk] = base + f;
   }
 }
 
@@ -1906,7 +1946,7 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 4) board_fit_ke
   __shared__ float s_ext[2][2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int f = w.fit_order[blockIdx.x];  // big frames first, dealt to the SMs in snake order (fit_order_kernel)
+  const int f = w.fit_order[w.frame_base + blockIdx.x];  // big frames first, dealt to the SMs in snake order (fit_order_kernel)
   ilcc2_diag* d = w.diag + f;
   float* corners = w.corners + (size_t)f * p.ncorners * 3;
   const int st = d->status;
@@ -1961,6 +2001,10 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 4) board_fit_ke
     s_ext[warp][1] = zmax;
   }
   F.wbits = wbits;
+  F.timing = d->plane;
+#ifdef FIT_TIMING
+  if (tid < 4) F.timing[tid] = 0.f;
+#endif
   if (tid < 2) s_cost[tid] = 0.0;
   __syncthreads();
 
