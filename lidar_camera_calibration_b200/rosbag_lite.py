@@ -154,3 +154,33 @@ def first_cloud(path: str, topic: str = "/velodyne_points") -> PointCloud2:
     for _, msg in iter_messages(path, topic):
         return parse_pointcloud2(msg)
     raise ValueError(f"{path}: no message on {topic}")
+
+
+def write_pointcloud2_bag(path: str, records: np.ndarray, topic: str = "/velodyne_points", frame_id: str = "velodyne"):
+    """Write a one-message bag v2.0 (uncompressed chunk) holding `records` ((N,8) float32 = 32-byte velodyne records:
+    x@0 y@4 z@8 intensity@16 ring(u16)@20), in the layout of the bundled bags. Used to feed the C++ host tool in tests."""
+    rec = np.ascontiguousarray(records, np.float32)
+    assert rec.ndim == 2 and rec.shape[1] == 8
+
+    def hdr(fields):
+        b = b"".join(struct.pack("<I", len(k) + 1 + len(v)) + k.encode() + b"=" + v for k, v in fields)
+        return struct.pack("<I", len(b)) + b
+
+    def record(h, data):
+        return h + struct.pack("<I", len(data)) + data
+
+    n = rec.shape[0]
+    flds = [("x", 0, 7), ("y", 4, 7), ("z", 8, 7), ("intensity", 16, 7), ("ring", 20, 4)]
+    msg = struct.pack("<III", 0, 0, 0) + struct.pack("<I", len(frame_id)) + frame_id.encode() + struct.pack("<II", 1, n)
+    msg += struct.pack("<I", len(flds))
+    for name, off, dt in flds:
+        msg += struct.pack("<I", len(name)) + name.encode() + struct.pack("<IBI", off, dt, 1)
+    msg += struct.pack("<BII", 0, 32, 32 * n) + struct.pack("<I", 32 * n) + rec.tobytes() + struct.pack("<B", 1)
+    conn = record(hdr([("op", b"\x07"), ("conn", struct.pack("<I", 0)), ("topic", topic.encode())]),
+                  hdr([("type", b"sensor_msgs/PointCloud2"), ("topic", topic.encode())]))
+    m = record(hdr([("op", b"\x02"), ("conn", struct.pack("<I", 0)), ("time", struct.pack("<II", 1, 0))]), msg)
+    chunk = record(hdr([("op", b"\x05"), ("compression", b"none"), ("size", struct.pack("<I", len(conn + m)))]), conn + m)
+    with open(path, "wb") as f:
+        f.write(_MAGIC + record(hdr([("op", b"\x03"), ("chunk_count", struct.pack("<I", 1)),
+                                     ("conn_count", struct.pack("<I", 1)), ("index_pos", struct.pack("<Q", 0))]), b" " * 16))
+        f.write(chunk)

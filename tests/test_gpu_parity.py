@@ -140,3 +140,77 @@ def test_reference_shaped_class(api, bag_clouds, fixtures, tmp_path):
     out = tmp_path / "pointgrey_lidar_5.txt"
     api.save_corners2txt(est.m_cloud_corners, str(out))
     assert np.allclose(np.loadtxt(out), est.m_cloud_corners, rtol=1e-5, atol=1e-6)
+
+
+def test_cpp_host_tool_writes_the_reference_output_files(api, bag_clouds, fixtures, tmp_path):
+    """The C++ host tool (same I/O contract as the get_lidar_corners node: bags in, process_data/*.txt out) against
+    the shipped corner files, fed with bags rebuilt from the golden clouds."""
+    import os
+    import subprocess
+    from lidar_camera_calibration_b200 import rosbag_lite as rb
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tool = os.path.join(root, "lidar_camera_calibration_b200", "host", "get_lidar_corners")
+    if not os.path.exists(tool):
+        subprocess.check_call(["make", "-C", os.path.join(root, "lidar_camera_calibration_b200", "csrc"), "-s"])
+    (tmp_path / "pointgrey.yaml").write_text(fixtures["yaml_text"])
+    lines = []
+    for b in range(1, 7):
+        rb.write_pointcloud2_bag(str(tmp_path / f"2018-12-03-{b}.bag"), bag_clouds[b])
+        if str(b) in fixtures["key_flags"]:
+            c = np.asarray(fixtures["lidar_corners"][str(b)]).mean(0)
+            lines.append(f"{c[0]:.6f} {c[1]:.6f} {c[2]:.6f} {'d' if fixtures['key_flags'][str(b)] else ''}")
+        else:
+            lines.append("")                      # bag 4 has no fixture: skipped
+    (tmp_path / "clicks.txt").write_text("\n".join(lines) + "\n")
+    out = tmp_path / "process_data"
+    out.mkdir()
+    r = subprocess.run([tool, "--bag-prefix", str(tmp_path / "2018-12-03-"), "--bag-num", "6", "--yaml",
+                        str(tmp_path / "pointgrey.yaml"), "--camera", "pointgrey", "--clicks", str(tmp_path / "clicks.txt"),
+                        "--out-dir", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    for b in fixtures["key_flags"]:
+        got = np.loadtxt(out / f"pointgrey_lidar_{b}.txt")
+        fx = np.asarray(fixtures["lidar_corners"][b])
+        assert got.shape == (35, 3) and np.linalg.norm(got - fx, axis=1).max() < 7e-3
+    assert not (out / "pointgrey_lidar_4.txt").exists()
+
+
+def test_hdl64_like_frames_9x7_board(api, oracle):
+    """BASELINE.json config 4: 64 rings x 2048 azimuths, 9x7 board: ROI ~12-16 k points (> the shared-memory
+    clustering capacity -> global-memory path), ~10-14 k optimiser points (> the shared-memory bit capacity)."""
+    from lidar_camera_calibration_b200 import synth
+    F = 3
+    pts, clicks, gt = synth.make_batch(F, scene=synth.SCENE_HDL64, want_truth=True)
+    p_g = api.default_params(cells_x=8, cells_y=10)
+    p_o = oracle.default_params(cells_x=8, cells_y=10)
+    ex = api.CornerExtractor(F, synth.HDL64.n_points, params=p_g)
+    st, corners, diags = ex.extract(pts, clicks, flags=api.FLAG_AUTO, want_diag=True)
+    assert corners.shape == (F, 63, 3)
+    for f in range(F):
+        st_o, c_o, d_o, roi_o, clu_o, brd_o = oracle.extract_frame(pts[f], clicks[f], flags=oracle.FLAG_AUTO, params=p_o,
+                                                                 want_indices=True)
+        assert st[f] == st_o == 0
+        assert np.array_equal(ex.fetch_indices(f, 0), roi_o)
+        assert np.array_equal(ex.fetch_indices(f, 1), clu_o)
+        assert np.array_equal(ex.fetch_indices(f, 2), brd_o)
+        assert np.array_equal(diags[f]["pca"], d_o["pca"]) and diags[f]["n_opt"] == d_o["n_opt"] > 8192
+        assert np.linalg.norm(corners[f].astype(np.float64) - c_o, axis=1).max() <= TOL_CORNER_M
+
+
+def test_solver_state_agrees_with_oracle(api, oracle):
+    """theta, t and the Huber cost of both colour hypotheses: the GPU sums group the residuals differently from the
+    oracle (dense candidate lists vs. all points), so agreement is to rounding, not bitwise."""
+    from lidar_camera_calibration_b200 import synth
+    F = 24
+    pts, clicks = synth.make_batch(F, start=500)
+    ex = api.CornerExtractor(F, synth.VLP16.n_points)
+    st, corners, diags = ex.extract(pts, clicks, flags=api.FLAG_AUTO, want_diag=True)
+    st_o, corners_o, diags_o = oracle.extract_batch(pts, clicks, flags=oracle.FLAG_AUTO, threads=4, want_diag=True)
+    assert np.array_equal(st, st_o)
+    for f in range(F):
+        if st[f] != 0:
+            continue
+        assert np.array_equal(diags[f]["iters"], diags_o[f]["iters"]) and np.array_equal(diags[f]["term"], diags_o[f]["term"])
+        assert np.allclose(diags[f]["theta_t"], diags_o[f]["theta_t"], rtol=0, atol=1e-9)
+        assert np.allclose(diags[f]["cost"], diags_o[f]["cost"], rtol=1e-9, atol=1e-12)
+        assert np.abs(corners[f].astype(np.float64) - corners_o[f]).max() < 1e-6
