@@ -89,6 +89,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads() -> int:
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1, so ask the scheduler instead)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def make_workload(n_frames: int, start: int):
     from lidar_camera_calibration_b200 import synth
     t = time.time()
@@ -112,7 +120,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle as O
-    threads = O.max_threads()
+    threads = host_threads()
     sample = args.ref_sample_frames
     pts, clicks, _ = make_workload(sample, 0)
     for _ in range(args.warmup):
@@ -279,8 +287,7 @@ def main():
         "workload_gen_s": gen_s,
     }
     if not args.no_cpu_baseline and world == 1:
-        from oracle import oracle as O
-        threads = O.max_threads()
+        threads = host_threads()
         v, n, ok = cpu_baseline(pts, clicks, args.cpu_sample_frames, threads)
         v1, n1, _ = cpu_baseline(pts, clicks, max(8, args.cpu_sample_frames // 16), 1)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
