@@ -43,6 +43,26 @@ def hbm_peak():
         return HBM_FALLBACK_GBS, "fallback"
 
 
+def ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel from the committed
+    `ncu --set full` summaries under profiles/ (same workload: 1024 frames). Returns {stage: bytes}."""
+    import glob
+    import re
+    out = {}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_*_r1c.txt"))):
+        name = None
+        for line in open(path):
+            m = re.match(r"== (?:void )?(\w+?)(?:_kernel)?(?:<(\d)>)?\(", line)
+            if m:
+                name = m.group(1) if m.group(2) in (None, "1") or m.group(1) == "roi_filter" else None
+                continue
+            m = re.search(r"dram__bytes_(read|write)\.sum = ([0-9.]+) (\w+)", line)
+            if m and name:
+                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m.group(3)]
+                out[name] = out.get(name, 0.0) + float(m.group(2)) * mult
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -260,7 +280,8 @@ def main():
         a = bytes_launch / (ms * 1e-3) / 1e9
         return {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak}
 
-    roofline = dict(roof(per_launch_ms[dom]), traffic=None, kernel=dom, peak_source=f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+    traffic = ncu_traffic() if F == 1024 else {}
+    roofline = dict(roof(per_launch_ms[dom]), traffic=traffic.get(dom), kernel=dom, peak_source=f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
                     algorithmic_bytes_per_launch=bytes_launch, kernel_ms_per_launch=per_launch_ms[dom],
                     share_of_step=stage_ms[dom] / sum(stage_ms.values()))
     out = {
@@ -281,7 +302,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_path": dict(roof(elapsed_ms / K), note="whole step, all five kernels"),
-        "roofline_k1": dict(roof(per_launch_ms["roi_filter"]), kernel="roi_filter",
+        "roofline_k1": dict(roof(per_launch_ms["roi_filter"]), kernel="roi_filter", traffic=traffic.get("roi_filter"),
                             note="the only kernel that reads all input bytes"),
         "kernel_ms_per_step": per_launch_ms,
         "workload_gen_s": gen_s,

@@ -105,6 +105,7 @@ typedef struct ilcc2_diag {
   double gray[2];            /* gray_zone (:322-323) */
   double theta_t[2][3];      /* per hypothesis: theta, t_y, t_z */
   double cost[2];            /* per hypothesis: final Huber cost of the second phase */
+  double cost_a[2];          /* per hypothesis: final Huber cost of the first (useOutofBoard) phase */
 } ilcc2_diag;
 
 typedef struct ilcc2_handle ilcc2_handle;

@@ -61,7 +61,10 @@ struct ilcc2_handle {
   static constexpr int kMaxChunks = 64;
   cudaEvent_t ev_copied[kMaxChunks] = {};
   cudaEvent_t ev_start = nullptr;
-  int e2e_chunk_frames = 512;
+  static constexpr int kWorkStreams = 4;   // chunks are computed round-robin on these, so their kernels overlap
+  cudaStream_t work_stream[kWorkStreams] = {};
+  cudaEvent_t ev_work_done[kWorkStreams] = {};
+  int e2e_chunk_frames = 256;
   bool ev_valid = false;
   int64_t launches = 0;
   std::string error;
@@ -274,6 +277,10 @@ int ilcc2_create(const ilcc2_params* params, int device, int max_frames, int max
   for (int i = 0; i < ilcc2_handle::kMaxChunks && ce == cudaSuccess; ++i)
     A(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
   if (ce == cudaSuccess) A(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+  for (int i = 0; i < ilcc2_handle::kWorkStreams && ce == cudaSuccess; ++i) {
+    A(cudaStreamCreateWithFlags(&h->work_stream[i], cudaStreamNonBlocking));
+    A(cudaEventCreateWithFlags(&h->ev_work_done[i], cudaEventDisableTiming));
+  }
   if (const char* e = getenv("ILCC2_E2E_CHUNK")) h->e2e_chunk_frames = atoi(e) > 0 ? atoi(e) : h->e2e_chunk_frames;
   if (ce != cudaSuccess) {
     const int rc = fail(nullptr, ILCC2_ERR_CUDA, "ilcc2_create: %s", cudaGetErrorString(ce));
@@ -299,6 +306,10 @@ int ilcc2_destroy(ilcc2_handle* h) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int i = 0; i < ilcc2_handle::kWorkStreams; ++i) {
+    if (h->work_stream[i]) cudaStreamDestroy(h->work_stream[i]);
+    if (h->ev_work_done[i]) cudaEventDestroy(h->ev_work_done[i]);
+  }
   delete h;
   return ILCC2_SUCCESS;
 }
@@ -405,11 +416,13 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
     }
     return cudaSuccess;
   };
-  // Host buffers: the batch is cut into chunks of frames; chunk c+1 is copied on the copy stream while the five
-  // kernels of chunk c run on the caller's stream (needs page-locked host memory to actually overlap).
-  // Device buffers, profiling runs and ragged batches: one chunk.
+  // Host buffers: the batch is cut into chunks of frames.  Chunks are copied back to back on a private copy stream
+  // and computed round-robin on private work streams, so the five kernels of chunk c overlap both the copy of the
+  // following chunks and the kernels of its neighbours (a small chunk leaves most SMs idle on its own: its run
+  // time is the latency of its slowest frame).  Needs page-locked host memory to actually overlap.
+  // Device buffers, profiling runs and ragged batches: one chunk on the caller's stream.
   int chunk = n_frames;
-  if (mem_kind == ILCC2_MEM_HOST && !prof && !frame_offsets && n_frames > h->e2e_chunk_frames) {
+  if (mem_kind == ILCC2_MEM_HOST && !prof && !debug_sync && !frame_offsets && n_frames > h->e2e_chunk_frames) {
     chunk = h->e2e_chunk_frames;
     while ((n_frames + chunk - 1) / chunk > ilcc2_handle::kMaxChunks) chunk *= 2;
   }
@@ -418,8 +431,9 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
     if (n_chunks == 1) {
       CU_TRY(h, cudaMemcpyAsync(h->d_points_stage, points, bytes, cudaMemcpyHostToDevice, s));
     } else {
-      CU_TRY(h, cudaEventRecord(h->ev_start, s));
+      CU_TRY(h, cudaEventRecord(h->ev_start, s));  // everything queued on s so far (small copies, memset) comes first
       CU_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_start, 0));
+      for (int i = 0; i < ilcc2_handle::kWorkStreams; ++i) CU_TRY(h, cudaStreamWaitEvent(h->work_stream[i], h->ev_start, 0));
       const size_t frame_bytes = (size_t)points_per_frame * point_step;
       for (int c = 0; c < n_chunks; ++c) {
         const int f0 = c * chunk, nf = (f0 + chunk <= n_frames) ? chunk : n_frames - f0;
@@ -434,18 +448,25 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
   for (int c = 0; c < n_chunks; ++c) {
     w.frame_base = c * chunk;
     w.n_frames = (w.frame_base + chunk <= n_frames) ? chunk : n_frames - w.frame_base;
-    if (n_chunks > 1) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_copied[c], 0));
-    launch_roi_filter(w, h->dp, s);
+    cudaStream_t cs = n_chunks > 1 ? h->work_stream[c % ilcc2_handle::kWorkStreams] : s;
+    if (n_chunks > 1) CU_TRY(h, cudaStreamWaitEvent(cs, h->ev_copied[c], 0));
+    launch_roi_filter(w, h->dp, cs);
     if (n_chunks == 1) CU_TRY(h, stage_done(1));
-    launch_cluster(w, h->dp, s);
+    launch_cluster(w, h->dp, cs);
     if (n_chunks == 1) CU_TRY(h, stage_done(2));
-    launch_plane(w, h->dp, s);
+    launch_plane(w, h->dp, cs);
     if (n_chunks == 1) CU_TRY(h, stage_done(3));
-    launch_pca_gray(w, h->dp, s);
+    launch_pca_gray(w, h->dp, cs);
     if (n_chunks == 1) CU_TRY(h, stage_done(4));
-    launch_board_fit(w, h->dp, s);
+    launch_board_fit(w, h->dp, cs);
     if (n_chunks == 1) CU_TRY(h, stage_done(5));
     h->launches += kStages + 1 + (h->cap > kFitBitsCap ? 1 : 0) + (h->cap > kClusterSmemPts ? 1 : 0);
+  }
+  if (n_chunks > 1) {  // join the work streams back into the caller's stream
+    for (int i = 0; i < ilcc2_handle::kWorkStreams; ++i) {
+      CU_TRY(h, cudaEventRecord(h->ev_work_done[i], h->work_stream[i]));
+      CU_TRY(h, cudaStreamWaitEvent(s, h->ev_work_done[i], 0));
+    }
   }
   h->ev_valid = prof;
   CU_TRY(h, cudaGetLastError());

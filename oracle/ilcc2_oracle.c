@@ -1488,6 +1488,7 @@ int ilcc2o_extract_frame(const void* points, int32_t n, int32_t point_step,
         D.term[h][phase] = solve_tr(&Pb, P->max_solver_iterations, x, &fc, &it);
         D.iters[h][phase] = it;
         D.cost[h] = fc;
+        if (phase == 0) D.cost_a[h] = fc;
         evals += Pb.n_evals;
       }
       D.n_evals[h] = evals;

@@ -95,6 +95,7 @@ typedef struct ilcc2o_diag {
   double gray[2];
   double theta_t[2][3];
   double cost[2];
+  double cost_a[2];          /* per hypothesis: final Huber cost of the first (useOutofBoard) phase */
 } ilcc2o_diag;
 
 void ilcc2o_default_params(ilcc2o_params* p);

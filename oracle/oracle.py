@@ -47,7 +47,7 @@ class Diag(C.Structure):
         ("plane", C.c_float * 4), ("pca", C.c_float * 16), ("eigvals", C.c_float * 3),
         ("hist_min", C.c_double), ("hist_max", C.c_double), ("hist_mean", C.c_double),
         ("r_low", C.c_double), ("r_high", C.c_double), ("gray", C.c_double * 2),
-        ("theta_t", (C.c_double * 3) * 2), ("cost", C.c_double * 2),
+        ("theta_t", (C.c_double * 3) * 2), ("cost", C.c_double * 2), ("cost_a", C.c_double * 2),
     ]
 
 
