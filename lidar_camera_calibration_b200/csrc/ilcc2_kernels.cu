@@ -1336,6 +1336,26 @@ __device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
 // sincos() inlines a large slow path; keep one copy of it in the kernel
 __device__ __noinline__ void sincos_once(double x, double* s, double* c) { sincos(x, s, c); }
 
+// Cheap reciprocal / square root for the INSIDE of self-correcting iterations (the secular-equation Newton of
+// tr_boundary_2d): MUFU seed (about 20 bits) + two Newton steps, about 1-2 ulp, 6-9 instructions instead of the
+// ~50 of the IEEE sequences.  Arguments there are finite, positive and far from the exponent limits.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+__device__ __forceinline__ double fast_sqrt_pos(double a) {  // a > 0
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  y = y * fma(-0.5 * a * y, y, 1.5);
+  y = y * fma(-0.5 * a * y, y, 1.5);
+  double g = a * y;
+  g = fma(0.5 * y, fma(-g, g, a), g);
+  return g;
+}
+
 __device__ __forceinline__ double huber_cost(const VbModel& M, double r) {
   const double sq = r * r;
   return (sq > M.hb) ? 0.5 * (M.two_ha * r - M.hb) : 0.5 * sq;
@@ -1450,17 +1470,25 @@ __device__ __forceinline__ void list_pass(const float2* __restrict__ yz, const u
                                           const IdxT* list, int list_cap, const VbModel& M, bool oob, bool want_jac,
                                           double c, double s, double ty, double tz, int lane, int n1, int n2,
                                           double (&a)[9]) {
-  for (int e0 = 0; e0 < n1; e0 += 32) {  // L1: colour mismatch or not certain -> full residual
-    const int e = e0 + lane;
-    const bool act = e < n1;
-    const int k = act ? (int)list[e] : 0;
-    const float2 q = __ldg(yz + k);
-    const unsigned wx = ((wbits[k >> 5] >> (k & 31)) & 1u) ^ (unsigned)M.tlw;
-    const double y = (double)q.x, z = (double)q.y;
-    double si, sj;
-    double r = vb_eval(M, oob, y, z, wx, c, s, ty, tz, si, sj);
-    if (!act) r = 0.0;
-    accumulate_point(M, want_jac, y, z, c, s, r, si, sj, a);
+#ifndef LIST_U
+#define LIST_U 1
+#endif
+  for (int e0 = 0; e0 < n1; e0 += 32 * LIST_U) {  // L1: colour mismatch or not certain -> full residual
+    double y[LIST_U], z[LIST_U], r[LIST_U], si[LIST_U], sj[LIST_U];
+#pragma unroll
+    for (int u = 0; u < LIST_U; ++u) {  // LIST_U independent points per lane: the fp64 chain is latency-bound
+      const int e = e0 + 32 * u + lane;
+      const bool act = e < n1;
+      const int k = act ? (int)list[e] : 0;
+      const float2 q = __ldg(yz + k);
+      const unsigned wx = ((wbits[k >> 5] >> (k & 31)) & 1u) ^ (unsigned)M.tlw;
+      y[u] = (double)q.x;
+      z[u] = (double)q.y;
+      r[u] = vb_eval(M, oob, y[u], z[u], wx, c, s, ty, tz, si[u], sj[u]);
+      if (!act) r[u] = 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < LIST_U; ++u) accumulate_point(M, want_jac, y[u], z[u], c, s, r[u], si[u], sj[u], a);
   }
   if (oob) {
     for (int e0 = 0; e0 < n2; e0 += 32) {  // L2: certainly outside the board -> distance to the nearest edges
@@ -1522,6 +1550,16 @@ __device__ bool tr2_eval(double a, double b, double dd, double g0, double g1, do
   const double ay = a + y, dy = dd + y;
   const double det = ay * dy - b * b;
   if (!(ay > 0.0) || !(det > 0.0)) return false;
+#ifdef FAST_TR2
+  if (det > 1e-280 && det < 1e280) {
+    const double inv = fast_rcp(det);
+    x[0] = -(dy * g0 - b * g1) * inv;
+    x[1] = -(ay * g1 - b * g0) * inv;
+    n2 = x[0] * x[0] + x[1] * x[1];
+    q = x[0] * ((dy * x[0] - b * x[1]) * inv) + x[1] * ((ay * x[1] - b * x[0]) * inv);
+    return true;
+  }
+#endif
   x[0] = ddiv(-(dy * g0 - b * g1), det);
   x[1] = ddiv(-(ay * g1 - b * g0), det);
   n2 = x[0] * x[0] + x[1] * x[1];
@@ -1549,6 +1587,9 @@ __device__ __noinline__ bool tr_boundary_2d(const double B[3], const double g[2]
   if (y < lo || y > hi) y = lo;
   double x[2] = {0.0, 0.0}, n2 = 0.0, q = 0.0;
   bool have = false;
+#ifdef FAST_TR2
+  const double inv_radius = ddiv(1.0, radius);
+#endif
   for (int it = 0; it < 100; ++it) {
     if (!tr2_eval(a, b, dd, g[0], g[1], y, x, n2, q)) {
       lo = y;
@@ -1557,10 +1598,18 @@ __device__ __noinline__ bool tr_boundary_2d(const double B[3], const double g[2]
       continue;
     }
     have = true;
+#ifdef FAST_TR2
+    const bool fast_ok = n2 > 1e-280 && n2 < 1e280 && fabs(q) > 1e-280 && fabs(q) < 1e280;
+    const double n = fast_ok ? fast_sqrt_pos(n2) : dsqrt(n2);
+    if (fabs(n - radius) <= 1e-14 * radius) break;
+    if (n > radius) lo = y; else hi = y;
+    double yn = fast_ok ? y + ((n - radius) * inv_radius) * (n2 * fast_rcp(q)) : y + ddiv(n - radius, radius) * ddiv(n2, q);
+#else
     const double n = dsqrt(n2);
     if (fabs(n - radius) <= 1e-14 * radius) break;
     if (n > radius) lo = y; else hi = y;
     double yn = y + ddiv(n - radius, radius) * ddiv(n2, q);
+#endif
     if (!(yn > lo && yn < hi)) yn = 0.5 * (lo + hi);
     if (yn == y || !(hi > lo)) break;
     y = yn;
@@ -2028,6 +2077,7 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 4) board_fit_ke
       double fc = 0.0;
       M.tlw = h;
       const int term0 = solve_tr<IdxT>(&F, &M, 1, p.max_solver_iter, lane, x, &fc, &it0, &evals);  // useOutofBoard
+      if (lane == 0) d->cost_a[h] = fc;
       const int term1 = solve_tr<IdxT>(&F, &M, 0, p.max_solver_iter, lane, x, &fc, &it1, &evals);  // then without
       if (lane == 0) {
         d->iters[h][0] = it0;

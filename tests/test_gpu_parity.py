@@ -213,4 +213,5 @@ def test_solver_state_agrees_with_oracle(api, oracle):
         assert np.array_equal(diags[f]["iters"], diags_o[f]["iters"]) and np.array_equal(diags[f]["term"], diags_o[f]["term"])
         assert np.allclose(diags[f]["theta_t"], diags_o[f]["theta_t"], rtol=0, atol=1e-9)
         assert np.allclose(diags[f]["cost"], diags_o[f]["cost"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(diags[f]["cost_a"], diags_o[f]["cost_a"], rtol=1e-9, atol=1e-12)
         assert np.abs(corners[f].astype(np.float64) - corners_o[f]).max() < 1e-6

@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported(product_lib):
 def test_struct_layouts_match_the_oracle_and_the_header(product_lib, oracle):
     from lidar_camera_calibration_b200 import _lib
     assert C.sizeof(_lib.Params) == C.sizeof(oracle.Params) == 96          # sizeof(ilcc2_params) in the header
-    assert C.sizeof(_lib.Diag) == C.sizeof(oracle.Diag) == 304             # sizeof(ilcc2_diag)
+    assert C.sizeof(_lib.Diag) == C.sizeof(oracle.Diag) == 320             # sizeof(ilcc2_diag)
     assert [f[0] for f in _lib.Diag._fields_] == [f[0] for f in oracle.Diag._fields_]
 
 
