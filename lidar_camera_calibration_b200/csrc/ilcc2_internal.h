@@ -36,7 +36,12 @@ constexpr int kClusterSmemSlots = 8192;
 constexpr int kClusterBitmapRows = 2944; // K2: occupancy bitmap rows (ncy*ncz) that fit the shared-memory layout
 constexpr int kClusterQueue = 160;       // K2: per-warp queue of (cell, neighbour) pairs: 32 lanes x 5 dx
 constexpr int kPlaneThreads = 128;    // K3/K4 CTA size == canonical reduction width of their double sums
-constexpr int kFitThreads = 64;       // K5: warp 0 = hypothesis topleftWhite=false, warp 1 = true
+#ifndef FIT_TEAM
+#define FIT_TEAM 2
+#endif
+constexpr int kFitTeam = FIT_TEAM;    // K5: warps that share one solve (one colour hypothesis of one frame)
+constexpr int kFitWarps = 2 * kFitTeam;  // K5: team 0 = hypothesis topleftWhite=false, team 1 = true
+constexpr int kFitThreads = 32 * kFitWarps;
 constexpr int kFitListCap = 3200;     // K5: per-warp candidate list buffer in shared memory = chunk length (multiple of 32)
 constexpr int kFitBitsCap = 8192;      // K5: colour bits kept in shared memory; larger frames take the global-memory path
 constexpr int kRndTable = 8192;       // PCL RANSAC draw table length

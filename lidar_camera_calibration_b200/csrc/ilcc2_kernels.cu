@@ -1330,11 +1330,8 @@ __device__ __forceinline__ double vb_eval_out(const VbModel& M, double y, double
 
 // IEEE double division / square root expand to ~50 instructions each at every use; the scalar solver below has
 // ~100 of them.  One out-of-line copy keeps the kernel image (and its instruction-cache footprint) small.
-__device__ __noinline__ double ddiv(double a, double b) { return a / b; }
-__device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
-
-// sincos() inlines a large slow path; keep one copy of it in the kernel
-__device__ __noinline__ void sincos_once(double x, double* s, double* c) { sincos(x, s, c); }
+__device__ __noinline__ double ddiv_ieee(double a, double b) { return a / b; }
+__device__ __noinline__ double dsqrt_ieee(double a) { return sqrt(a); }
 
 // Cheap reciprocal / square root for the INSIDE of self-correcting iterations (the secular-equation Newton of
 // tr_boundary_2d): MUFU seed (about 20 bits) + two Newton steps, about 1-2 ulp, 6-9 instructions instead of the
@@ -1355,6 +1352,36 @@ __device__ __forceinline__ double fast_sqrt_pos(double a) {  // a > 0
   g = fma(0.5 * y, fma(-g, g, a), g);
   return g;
 }
+
+#ifdef FAST_DIV
+// Scalar-solver division / square root as short sequences (MUFU seed + Newton + one residual correction): the
+// results are within 1 ulp of the IEEE ones (usually equal).  Arguments outside the safe exponent range take the
+// IEEE path.  FAST_DIV=1 inlines them (independent divisions can overlap, larger image), FAST_DIV=2 keeps one copy.
+#if FAST_DIV == 2
+#define FAST_DIV_INLINE __noinline__
+#else
+#define FAST_DIV_INLINE __forceinline__
+#endif
+__device__ FAST_DIV_INLINE double ddiv(double a, double b) {
+  const double ab = fabs(b);
+  if (ab > 1e-280 && ab < 1e280 && fabs(a) < 1e280) {
+    const double r = fast_rcp(b);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+  }
+  return ddiv_ieee(a, b);
+}
+__device__ FAST_DIV_INLINE double dsqrt(double a) {
+  if (a > 1e-280 && a < 1e280) return fast_sqrt_pos(a);
+  return dsqrt_ieee(a);
+}
+#else
+__device__ __forceinline__ double ddiv(double a, double b) { return ddiv_ieee(a, b); }
+__device__ __forceinline__ double dsqrt(double a) { return dsqrt_ieee(a); }
+#endif
+
+// sincos() inlines a large slow path; keep one copy of it in the kernel
+__device__ __noinline__ void sincos_once(double x, double* s, double* c) { sincos(x, s, c); }
 
 __device__ __forceinline__ double huber_cost(const VbModel& M, double r) {
   const double sq = r * r;
@@ -1550,7 +1577,7 @@ __device__ bool tr2_eval(double a, double b, double dd, double g0, double g1, do
   const double ay = a + y, dy = dd + y;
   const double det = ay * dy - b * b;
   if (!(ay > 0.0) || !(det > 0.0)) return false;
-#ifdef FAST_TR2
+#ifndef NO_FAST_TR2
   if (det > 1e-280 && det < 1e280) {
     const double inv = fast_rcp(det);
     x[0] = -(dy * g0 - b * g1) * inv;
@@ -1587,7 +1614,7 @@ __device__ __noinline__ bool tr_boundary_2d(const double B[3], const double g[2]
   if (y < lo || y > hi) y = lo;
   double x[2] = {0.0, 0.0}, n2 = 0.0, q = 0.0;
   bool have = false;
-#ifdef FAST_TR2
+#ifndef NO_FAST_TR2
   const double inv_radius = ddiv(1.0, radius);
 #endif
   for (int it = 0; it < 100; ++it) {
@@ -1598,7 +1625,7 @@ __device__ __noinline__ bool tr_boundary_2d(const double B[3], const double g[2]
       continue;
     }
     have = true;
-#ifdef FAST_TR2
+#ifndef NO_FAST_TR2
     const bool fast_ok = n2 > 1e-280 && n2 < 1e280 && fabs(q) > 1e-280 && fabs(q) < 1e280;
     const double n = fast_ok ? fast_sqrt_pos(n2) : dsqrt(n2);
     if (fabs(n - radius) <= 1e-14 * radius) break;
@@ -1740,6 +1767,30 @@ __device__ __noinline__ bool dogleg_compute_step(Dogleg& S, const double Hs[6], 
 
 enum { TERM_MAX_ITER = 0, TERM_GRADIENT = 1, TERM_PARAMETER = 2, TERM_FUNCTION = 3, TERM_MIN_RADIUS = 4, TERM_INVALID = 5 };
 
+// Sum of per-warp totals over the kFitTeam warps that share a solve.  Every warp of the team ends up with the
+// bit-identical total (fixed order: warp 0 of the team first), so the scalar solver can run redundantly on all of
+// them without any further exchange.  One named barrier per call; the slots are double-buffered (`parity`), which
+// is enough because a warp cannot run two reductions ahead of its team mates.
+template <int NQ>
+__device__ __forceinline__ void team_sum(double (&v)[NQ], double* slots /* [2][kFitTeam][9] of this team */, int team,
+                                         int wt, int lane, int& parity) {
+  if (kFitTeam == 1) return;
+  double* buf = slots + parity * (kFitTeam * 9);
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) buf[wt * 9 + q] = v[q];
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(32 * kFitTeam) : "memory");
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    double t = buf[q];
+#pragma unroll
+    for (int w = 1; w < kFitTeam; ++w) t += buf[w * 9 + q];
+    v[q] = t;
+  }
+  parity ^= 1;
+}
+
 // One ceres::Solve (TrustRegionMinimizer, Ceres 1.13/1.14 defaults) on one warp.  Written as a single loop
 // whose head evaluates the cost at the current candidate (the first candidate is the start point and is always
 // "accepted"), so that the classification / evaluation code exists exactly once in the kernel image.
@@ -1747,7 +1798,8 @@ enum { TERM_MAX_ITER = 0, TERM_GRADIENT = 1, TERM_PARAMETER = 2, TERM_FUNCTION =
 // iteration counter and radius advance exactly as if the same candidate had been evaluated and rejected again.
 template <typename IdxT>
 __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, int oob_i, int max_iter, int lane,
-                                     double* x, double* final_cost, int* iters_out, int* n_evals_io) {
+                                     double* x, double* final_cost, int* iters_out, int* n_evals_io, double* slots,
+                                     int* parity_io) {
   const float2* __restrict__ yz = Fp->yz;
   const uint32_t* wbits = Fp->wbits;
   IdxT* list = Fp->list;
@@ -1763,6 +1815,9 @@ __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, 
   const int n = Fp->n;
   const VbModel M = *Mp;
   const bool oob = oob_i != 0;
+  const int team = (threadIdx.x >> 5) / kFitTeam, wt = (threadIdx.x >> 5) % kFitTeam;
+  int parity = *parity_io;
+  const int team_cap = kFitTeam * list_cap;  // points per chunk: each warp of the team classifies / evaluates its share
 
   double xc[3] = {x[0], x[1], x[2]}, cand[3] = {x[0], x[1], x[2]};
   double g[3] = {0, 0, 0}, H[6] = {0, 0, 0, 0, 0, 0}, scale[3] = {1, 1, 1};
@@ -1791,18 +1846,24 @@ __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, 
 #pragma unroll
     for (int q = 0; q < 9; ++q) a[q] = 0.0;
     int n1 = 0, n2 = 0;
-    for (int k0 = 0; k0 < n; k0 += list_cap) {
+    for (int k0 = 0; k0 < n; k0 += team_cap) {
 #ifdef FIT_TIMING
       const long long tc0 = clock64();
 #endif
-      classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, cand[1], cand[2], lane, k0, min(k0 + list_cap, n), n1, n2);
+      // this warp's share of the chunk: a 32-aligned contiguous piece (may be empty)
+      const int k1 = min(k0 + team_cap, n);
+      const int piece = (((k1 - k0) + kFitTeam - 1) / kFitTeam + 31) & ~31;
+      const int ka = min(k0 + wt * piece, k1), kb = min(ka + piece, k1);
+      classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, cand[1], cand[2], lane, ka, kb, n1, n2);
 #ifdef FIT_TIMING
       t_cls += clock64() - tc0;
 #endif
       list_pass<IdxT>(yz, wbits, list, list_cap, M, oob, false, cs, sn, cand[1], cand[2], lane, n1, n2, a);
-      if (k0 + list_cap < n) __syncwarp();
+      if (k0 + team_cap < n) __syncwarp();
     }
-    const double cc = warp_butterfly(a[0]);
+    double cc1[1] = {warp_butterfly(a[0])};
+    team_sum<1>(cc1, slots, team, wt, lane, parity);
+    const double cc = cc1[0];
     n_evals++;
 #ifdef FIT_TIMING
     { const long long t1 = clock64(); t_eval += t1 - t0; t0 = t1; }
@@ -1825,17 +1886,21 @@ __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, 
       x_cost = cc;
 #pragma unroll
       for (int q = 0; q < 9; ++q) a[q] = 0.0;
-      if (n <= list_cap) {
+      if (n <= team_cap) {
         list_pass<IdxT>(yz, wbits, list, list_cap, M, oob, true, cs, sn, xc[1], xc[2], lane, n1, n2, a);
       } else {
-        for (int k0 = 0; k0 < n; k0 += list_cap) {
+        for (int k0 = 0; k0 < n; k0 += team_cap) {
           __syncwarp();
-          classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, xc[1], xc[2], lane, k0, min(k0 + list_cap, n), n1, n2);
+          const int k1 = min(k0 + team_cap, n);
+          const int piece = (((k1 - k0) + kFitTeam - 1) / kFitTeam + 31) & ~31;
+          const int ka = min(k0 + wt * piece, k1), kb = min(ka + piece, k1);
+          classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, xc[1], xc[2], lane, ka, kb, n1, n2);
           list_pass<IdxT>(yz, wbits, list, list_cap, M, oob, true, cs, sn, xc[1], xc[2], lane, n1, n2, a);
         }
       }
 #pragma unroll
       for (int q = 0; q < 9; ++q) a[q] = warp_butterfly(a[q]);
+      team_sum<9>(a, slots, team, wt, lane, parity);
       g[0] = a[0];
       g[1] = a[1];
       g[2] = a[2];
@@ -1912,6 +1977,7 @@ __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, 
   *final_cost = best_cost;
   *iters_out = iter;
   *n_evals_io += n_evals;
+  *parity_io = parity;
 #ifdef FIT_TIMING
   t_scalar += clock64() - t0;
   if (lane == 0) {
@@ -1984,15 +2050,16 @@ __global__ void __launch_bounds__(1024) fit_order_kernel(const Workspace w, int 
 //               frames above kFitListCap points are evaluated in chunks of kFitListCap)
 // SMEM = false: larger frames; same code on global-memory scratch.  Both are launched; each skips the other's frames.
 #ifndef FIT_MINB
-#define FIT_MINB 7
+#define FIT_MINB (kFitTeam == 1 ? 7 : 8 / kFitTeam)
 #endif
 template <bool SMEM>
-__global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 4) board_fit_kernel(const Workspace w, const DevParams p) {
+__global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : (kFitTeam == 1 ? 4 : 2)) board_fit_kernel(const Workspace w, const DevParams p) {
   using IdxT = typename std::conditional<SMEM, uint16_t, uint32_t>::type;
   extern __shared__ unsigned char fit_sm[];
   __shared__ double s_x[2][3];
   __shared__ double s_cost[2];
-  __shared__ float s_ext[2][2];
+  __shared__ float s_ext[kFitWarps][2];
+  __shared__ double s_red[2][2 * kFitTeam * 9];  // team_sum slots: [team][parity][warp of team][9]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int f = w.fit_order[w.frame_base + blockIdx.x];  // big frames first, dealt to the SMs in snake order (fit_order_kernel)
@@ -2067,19 +2134,28 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 4) board_fit_ke
   M.ha = p.huber_a;
   M.hb = p.huber_b;
   M.two_ha = 2.0 * p.huber_a;
-  M.ymax_zmax = fmaxf(s_ext[0][0], s_ext[1][0]) + fmaxf(s_ext[0][1], s_ext[1][1]);
-  if (autom || warp == 0) {
-    const int h_first = autom ? warp : 0;
-    const int h_last = autom ? warp : ((flags & ILCC2_FLAG_TOPLEFT_WHITE) ? 1 : 0);
+  {
+    float ym = 0.f, zm = 0.f;
+    for (int i = 0; i < kFitWarps; ++i) {
+      ym = fmaxf(ym, s_ext[i][0]);
+      zm = fmaxf(zm, s_ext[i][1]);
+    }
+    M.ymax_zmax = ym + zm;
+  }
+  const int team = warp / kFitTeam, wt = warp % kFitTeam;
+  if (autom || team == 0) {
+    const int h_first = autom ? team : 0;
+    const int h_last = autom ? team : ((flags & ILCC2_FLAG_TOPLEFT_WHITE) ? 1 : 0);
     double x[3] = {0.0, 0.0, 0.0};
+    int parity = 0;
     for (int h = h_first; h <= h_last; ++h) {  // manual mode: 'd' warm-starts hypothesis 1 from hypothesis 0
       int evals = 0, it0 = 0, it1 = 0;
       double fc = 0.0;
       M.tlw = h;
-      const int term0 = solve_tr<IdxT>(&F, &M, 1, p.max_solver_iter, lane, x, &fc, &it0, &evals);  // useOutofBoard
-      if (lane == 0) d->cost_a[h] = fc;
-      const int term1 = solve_tr<IdxT>(&F, &M, 0, p.max_solver_iter, lane, x, &fc, &it1, &evals);  // then without
-      if (lane == 0) {
+      const int term0 = solve_tr<IdxT>(&F, &M, 1, p.max_solver_iter, lane, x, &fc, &it0, &evals, s_red[team], &parity);  // useOutofBoard
+      if (lane == 0 && wt == 0) d->cost_a[h] = fc;
+      const int term1 = solve_tr<IdxT>(&F, &M, 0, p.max_solver_iter, lane, x, &fc, &it1, &evals, s_red[team], &parity);  // then without
+      if (lane == 0 && wt == 0) {
         d->iters[h][0] = it0;
         d->iters[h][1] = it1;
         d->term[h][0] = term0;
@@ -2128,7 +2204,7 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 4) board_fit_ke
 }
 
 size_t fit_smem_bytes() {
-  return sizeof(uint32_t) * (kFitBitsCap / 32) + 2 * sizeof(uint16_t) * kFitListCap;
+  return sizeof(uint32_t) * (kFitBitsCap / 32) + kFitWarps * sizeof(uint16_t) * kFitListCap;
 }
 
 void launch_board_fit(const Workspace& w, const DevParams& p, cudaStream_t s) {

@@ -877,8 +877,23 @@ typedef struct {
   int n_evals;
 } vb_problem;
 
+/* test-only trace of the evaluation points of a solve (per thread): 4 doubles per evaluation = x[0..2], kind
+ * (0 cost-only evaluation of a candidate, 1 cost + Jacobian at an accepted point) */
+static __thread double* g_trace = NULL;
+static __thread int g_trace_cap = 0, g_trace_n = 0;
+void ilcc2o_trace(double* buf, int cap) { g_trace = buf; g_trace_cap = cap; g_trace_n = 0; }
+int ilcc2o_trace_count(void) { return g_trace_n; }
+static void trace_eval(const double x[3], int kind) {
+  if (g_trace && g_trace_n < g_trace_cap) {
+    double* t = g_trace + 4 * (size_t)g_trace_n;
+    t[0] = x[0]; t[1] = x[1]; t[2] = x[2]; t[3] = (double)kind;
+  }
+  if (g_trace) g_trace_n++;
+}
+
 static double eval_cost(vb_problem* Pb, const double x[3]) {
   const vb_model* M = Pb->M;
+  trace_eval(x, 0);
   const double c = cos(x[0]), s = sin(x[0]);
   racc a;
   racc_zero_w(&a, RW_WARP);
@@ -898,6 +913,7 @@ static double eval_cost(vb_problem* Pb, const double x[3]) {
  * partial j mod 32 -- the order in which a warp walks the compacted list of non-zero residuals. */
 static void eval_jac(vb_problem* Pb, const double x[3], double* cost, double g[3], double H[6]) {
   const vb_model* M = Pb->M;
+  trace_eval(x, 1);
   const double c = cos(x[0]), s = sin(x[0]);
   racc a[10];
   for (int q = 0; q < 10; ++q) racc_zero_w(&a[q], RW_WARP);

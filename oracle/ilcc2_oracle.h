@@ -139,6 +139,26 @@ int ilcc2o_solve(const double* yz, const uint8_t* white, int32_t n, int W, int H
                  int topleft_white, int use_oob, double huber, int max_iter,
                  double x[3], double* final_cost, int32_t* iterations, int32_t* n_evals);
 
+/* ---- what follows the corner path in the reference: corner ordering and the LiDAR->camera PnP
+ *      (ilcc2_pnp_oracle.c; calib_lidar_cam.cpp:50-165, ImageCornersEst.cpp:430-505, Optimization.cpp:13-91) ---- */
+typedef struct ilcc2o_pnp_summary {
+  double initial_cost, final_cost;
+  int32_t iterations, termination, n_evals, n_pairs;
+} ilcc2o_pnp_summary;
+int ilcc2o_axis_roughly(const char* cam_name, double T_rowmajor[16]);
+void ilcc2o_order_lidar(double* pts3 /*[bw*bh][3], already in the rough camera axes*/, int bw, int bh);
+void ilcc2o_order_cam(double* pts2 /*[bw*bh][2]*/, int bw, int bh);
+void ilcc2o_pnp_residual(const double p3[3], const double p2[2], const double cam[4] /*fx cx fy cy*/,
+                         const double x[6] /*r, t*/, double res[2], double jac[12] /*nullable, 2 x 6*/);
+int ilcc2o_solve_pnp(const double* p3, const double* p2, const uint8_t* valid /*nullable*/, int32_t m,
+                     const double cam[4], double huber, int32_t max_iter, double r[3], double t[3],
+                     ilcc2o_pnp_summary* out);
+void ilcc2o_compose_extrinsic(const double r[3], const double t[3], const double T_axis[16], double T_out[16]);
+
+/* test-only: record the evaluation points of the solves run by the calling thread (4 doubles each: x[0..2], kind) */
+void ilcc2o_trace(double* buf, int cap);
+int ilcc2o_trace_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,11 +59,16 @@ def diag_to_dict(d: Diag) -> dict:
     return out
 
 
+class PnpSummary(C.Structure):
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double), ("iterations", C.c_int32),
+                ("termination", C.c_int32), ("n_evals", C.c_int32), ("n_pairs", C.c_int32)]
+
+
 def build(force: bool = False) -> str:
     """Compile the oracle with its Makefile (gcc). Returns the library path."""
     if force or not os.path.exists(_LIB_PATH) or any(
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
-            for f in ("ilcc2_oracle.c", "ilcc2_oracle.h", "Makefile")):
+            for f in ("ilcc2_oracle.c", "ilcc2_pnp_oracle.c", "ilcc2_oracle.h", "Makefile")):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB_PATH
 
@@ -100,6 +105,15 @@ def lib() -> C.CDLL:
         L.ilcc2o_solve.restype = C.c_int
         L.ilcc2o_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                    C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ilcc2o_axis_roughly.restype = C.c_int
+        L.ilcc2o_axis_roughly.argtypes = [C.c_char_p, C.c_void_p]
+        L.ilcc2o_order_lidar.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ilcc2o_order_cam.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ilcc2o_pnp_residual.argtypes = [C.c_void_p] * 6
+        L.ilcc2o_solve_pnp.restype = C.c_int
+        L.ilcc2o_solve_pnp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_double,
+                                       C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(PnpSummary)]
+        L.ilcc2o_compose_extrinsic.argtypes = [C.c_void_p] * 4
         _lib = L
     return _lib
 
@@ -227,3 +241,84 @@ def solve(yz: np.ndarray, white: np.ndarray, x0, W=6, H=8, g=0.15, topleft_white
     term = lib().ilcc2o_solve(yz.ctypes.data, white.ctypes.data, white.size, W, H, g, int(topleft_white),
                               int(use_oob), huber, max_iter, x.ctypes.data, C.byref(cost), C.byref(it), C.byref(ne))
     return term, x, cost.value, it.value, ne.value
+
+
+# ---- corner ordering + LiDAR->camera PnP (ilcc2_pnp_oracle.c) ----
+def axis_roughly(cam_name: str) -> np.ndarray:
+    """get_lidar2cam_axis_roughly (calib_lidar_cam.cpp:50-70) as a 4x4."""
+    T = np.zeros((4, 4))
+    lib().ilcc2o_axis_roughly(cam_name.encode(), T.ctypes.data)
+    return T
+
+
+def order_lidar(pts3: np.ndarray, bw: int, bh: int) -> np.ndarray:
+    p = np.ascontiguousarray(pts3, np.float64).copy()
+    lib().ilcc2o_order_lidar(p.ctypes.data, bw, bh)
+    return p
+
+
+def order_cam(pts2: np.ndarray, bw: int, bh: int) -> np.ndarray:
+    p = np.ascontiguousarray(pts2, np.float64).copy()
+    lib().ilcc2o_order_cam(p.ctypes.data, bw, bh)
+    return p
+
+
+def pnp_residual(p3, p2, cam, x, want_jac=True):
+    p3, p2, cam, x = (np.ascontiguousarray(a, np.float64) for a in (p3, p2, cam, x))
+    res, jac = np.zeros(2), np.zeros((2, 6))
+    lib().ilcc2o_pnp_residual(p3.ctypes.data, p2.ctypes.data, cam.ctypes.data, x.ctypes.data, res.ctypes.data,
+                              jac.ctypes.data if want_jac else None)
+    return res, jac
+
+
+def solve_pnp(p3, p2, cam, r0=(0, 0, 0), t0=(0, 0, 0), valid=None, huber=0.1, max_iter=50):
+    """Optimization::solvePose3d2dError (Optimization.cpp:13-91). Returns (r, t, summary dict)."""
+    p3, p2, cam = (np.ascontiguousarray(a, np.float64) for a in (p3, p2, cam))
+    r, t = np.array(r0, np.float64), np.array(t0, np.float64)
+    v = None if valid is None else np.ascontiguousarray(valid, np.uint8)
+    sm = PnpSummary()
+    lib().ilcc2o_solve_pnp(p3.ctypes.data, p2.ctypes.data, None if v is None else v.ctypes.data, p3.shape[0],
+                           cam.ctypes.data, huber, max_iter, r.ctypes.data, t.ctypes.data, C.byref(sm))
+    return r, t, {k: getattr(sm, k) for k, _ in PnpSummary._fields_}
+
+
+def compose_extrinsic(r, t, T_axis) -> np.ndarray:
+    r, t, T_axis = (np.ascontiguousarray(a, np.float64) for a in (r, t, T_axis))
+    T = np.zeros((4, 4))
+    lib().ilcc2o_compose_extrinsic(r.ctypes.data, t.ctypes.data, T_axis.ctypes.data, T.ctypes.data)
+    return T
+
+
+def read_cam_corners(path: str, num: int, board_h: int) -> np.ndarray:
+    """ImageCornersEst::read_cam_corners (ImageCornersEst.cpp:213-279): lines of x until >= num values, then lines
+    of y into the same [row][col]; emitted column-major when the row count differs from the board height."""
+    lines = [ln.split() for ln in open(path).read().splitlines()]
+    rows, counter, i = [], 0, 0
+    while i < len(lines):
+        vals = [float(v) for v in lines[i]]
+        i += 1
+        rows.append([[v, 0.0] for v in vals])
+        counter += len(vals)
+        if counter >= num:
+            break
+    k = 0
+    while i < len(lines) and k < len(rows):
+        for j, v in enumerate(lines[i][:len(rows[k])]):
+            rows[k][j][1] = float(v)
+        i += 1
+        k += 1
+    out = []
+    if len(rows) != board_h:
+        for w in range(len(rows[0])):
+            for h in range(len(rows)):
+                out.append(rows[h][w])
+    else:
+        for h in range(len(rows)):
+            out.extend(rows[h])
+    return np.asarray(out, np.float64)
+
+
+def read_lidar_corners(path: str, num: int) -> np.ndarray:
+    """ImageCornersEst::read_lidar_corners (:281-299): whitespace-separated floats parsed as float32."""
+    v = np.array(open(path).read().split()[: 3 * num], dtype=np.float32).reshape(-1, 3)
+    return v.astype(np.float64)

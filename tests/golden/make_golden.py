@@ -34,6 +34,10 @@ def main(ref="/root/reference"):
         fx["lidar_corners"][str(b)] = np.loadtxt(f"{ref}/ilcc2/process_data/pointgrey_lidar_{b}.txt").tolist()
         fx["cam_corners"][str(b)] = np.loadtxt(f"{ref}/ilcc2/process_data/pointgrey{b}.txt").tolist()
     fx["lidar_corner_text_1"] = open(f"{ref}/ilcc2/process_data/pointgrey_lidar_1.txt").read()
+    # raw text of every corner file, so that the tests can lay out a process_data/ directory for the host tools
+    fx["lidar_corner_text"] = {str(b): open(f"{ref}/ilcc2/process_data/pointgrey_lidar_{b}.txt").read() for b in range(1, 7)}
+    fx["cam_corner_text"] = {str(b): open(f"{ref}/ilcc2/process_data/pointgrey{b}.txt").read() for b in range(1, 7)}
+    fx["extrinsic_bin_hex"] = open(f"{ref}/ilcc2/config/pointgrey.bin", "rb").read().hex()
     import cv2
     fs = cv2.FileStorage(f"{ref}/ilcc2/config/pointgrey.yaml", cv2.FILE_STORAGE_READ)
     fx["yaml"] = {

@@ -7,7 +7,7 @@ if sys.argv[1] == "--child":
     import numpy as np, torch
     from lidar_camera_calibration_b200 import api, synth
     name, F = sys.argv[2], int(sys.argv[3])
-    cache = os.path.join(ROOT, "gpurun_out", f"ab_inputs_{F}.npz")
+    cache = f"/tmp/ab_inputs_{F}.npz"
     if os.path.exists(cache):
         z = np.load(cache); pts, clicks = z["pts"], z["clicks"]
     else:
@@ -33,7 +33,7 @@ if sys.argv[1] == "--child":
     e1.record(); torch.cuda.synchronize()
     st, c, d = ex.extract(pts, clicks, flags=api.FLAG_AUTO, want_diag=True)
     it = np.array([x["iters"] for x in d]).reshape(F, -1); th = np.array([x["theta_t"] for x in d]).reshape(F, -1)
-    ref = os.path.join(ROOT, "gpurun_out", f"ab_ref_{F}.npz")
+    ref = f"/tmp/ab_ref_{F}.npz"
     msg = ""
     if os.path.exists(ref):
         z = np.load(ref)
