@@ -175,6 +175,61 @@ int ilcc2_save_corners2txt(const float* corners_xyz, int n_corners, const char* 
 /* Frame sharding across ranks (one process per GPU): contiguous blocks. */
 void ilcc2_shard_range(int n_frames, int world_size, int rank, int* begin, int* count);
 
+/* =====================================================================================================
+ * What follows the corner path in the reference: ordering the 3-D / 2-D corners
+ * and the LiDAR->camera pose solve of ilcc2/test/calib_lidar_cam.cpp:101-165.  Kernels: csrc/ilcc2_pnp.cu.
+ * ===================================================================================================== */
+typedef struct ilcc2_pnp ilcc2_pnp;
+
+typedef struct ilcc2_pnp_summary { /* ceres::Solver::Summary of Optimization.cpp:68-69, the fields the node prints */
+  double initial_cost, final_cost;
+  int32_t iterations;  /* trust-region iterations (successful + unsuccessful) */
+  int32_t termination; /* 0 max iterations, 1 gradient, 2 parameter, 3 function tolerance, 4 radius, 5 invalid steps */
+  int32_t n_evals;     /* residual + Jacobian evaluations as Ceres counts them */
+  int32_t n_pairs;     /* -1: not counted on the device */
+} ilcc2_pnp_summary;
+
+int ilcc2_pnp_create(int device, ilcc2_pnp** out);
+int ilcc2_pnp_destroy(ilcc2_pnp* h);
+const char* ilcc2_pnp_last_error(const ilcc2_pnp* h);
+int64_t ilcc2_pnp_launch_count(const ilcc2_pnp* h);
+
+/* get_lidar2cam_axis_roughly (calib_lidar_cam.cpp:50-70): row-major 4x4 for camera_name in
+ * front / car_left / pointgrey / left / right / back; ILCC2_ERR_INVALID_ARGUMENT otherwise. Host only. */
+int ilcc2_axis_roughly(const char* camera_name, double T_rowmajor[16]);
+
+/* The "data ready" loop of calib_lidar_cam.cpp:119-123 for a batch of frames, on the device:
+ *   pts3_out[f][k]  = check_order_lidar(T_axis * (double)lidar_corners[f][k])   (ImageCornersEst.cpp:461-487)
+ *   pts2_out[f][k]  = check_order_cam(cam_corners[f][k])                        (ImageCornersEst.cpp:430-459)
+ *   valid_out[f*nc+k] = status == NULL || status[f] == ILCC2_OK                 (nullable)
+ * lidar_corners [n_frames][board_w*board_h][3] float32 as ilcc2_extract_corners writes them (board_w = the inner
+ * lattice index, e.g. 7; board_h = 5); cam_corners / pts2_out nullable.  T_axis is a HOST pointer.
+ * mem_kind: where lidar_corners / status / cam_corners / *_out live. */
+int ilcc2_pnp_order_corners(ilcc2_pnp* h, const float* lidar_corners, const int32_t* status, const double* cam_corners,
+                            int n_frames, int board_w, int board_h, const double T_axis[16], double* pts3_out,
+                            double* pts2_out, uint8_t* valid_out, int mem_kind, void* stream);
+
+/* Optimization::solvePose3d2dError (Optimization.cpp:13-91): Huber(huber_delta) reprojection error of pts3 under
+ * (angle-axis r, translation t) against pts2 with camera = fx, cx, fy, cy; Ceres trust region / dense normal
+ * Cholesky / subspace dogleg with its defaults (max_iterations 50 in the reference).
+ * pts3 [n_pairs][3], pts2 [n_pairs][2] float64, valid [n_pairs] (nullable) live where mem_kind says; camera, r, t
+ * (in: start, out: result) and summary are HOST pointers.  The call returns when the result is valid. */
+int ilcc2_pnp_solve(ilcc2_pnp* h, const double* pts3, const double* pts2, const uint8_t* valid, int n_pairs,
+                    const double camera[4], double huber_delta, int max_iterations, double r[3], double t[3],
+                    ilcc2_pnp_summary* summary, int mem_kind, void* stream);
+
+/* T_lidar2cam = [AngleAxis(|r|, r/|r|) | t] * T_axis_roughly (Optimization.cpp:75-88, calib_lidar_cam.cpp:157-160). */
+int ilcc2_compose_extrinsic(const double r[3], const double t[3], const double T_axis[16], double T_out_rowmajor[16]);
+
+/* ImageCornersEst::extrinsic2txt (ImageCornersEst.cpp:301-306): 128 bytes, Eigen::Matrix4d column-major. */
+int ilcc2_extrinsic2bin(const char* path, const double T_rowmajor[16]);
+
+/* The reference's text readers (ImageCornersEst.cpp:213-299) and camK of getRectifyParam (:15-31). Host only.
+ * The two corner readers return the number of corners read, or a negative ILCC2_ERR_*. */
+int ilcc2_read_cam_corners(const char* path, int num, int board_h, double* out_xy, int cap);
+int ilcc2_read_lidar_corners(const char* path, int num, double* out_xyz);
+int ilcc2_read_camera_yaml(const char* path, double K_rowmajor[9], int* corner_in_x, int* corner_in_y);
+
 #ifdef __cplusplus
 }
 #endif

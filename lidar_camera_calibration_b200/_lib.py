@@ -16,6 +16,9 @@ EXPORTS = [
     "ilcc2_version", "ilcc2_default_params", "ilcc2_set_chessboard_param", "ilcc2_create", "ilcc2_destroy",
     "ilcc2_last_error", "ilcc2_extract_corners", "ilcc2_fetch_indices", "ilcc2_fetch_board_points",
     "ilcc2_set_profiling", "ilcc2_stage_times", "ilcc2_launch_count", "ilcc2_save_corners2txt", "ilcc2_shard_range",
+    "ilcc2_pnp_create", "ilcc2_pnp_destroy", "ilcc2_pnp_last_error", "ilcc2_pnp_launch_count", "ilcc2_axis_roughly",
+    "ilcc2_pnp_order_corners", "ilcc2_pnp_solve", "ilcc2_compose_extrinsic", "ilcc2_extrinsic2bin",
+    "ilcc2_read_cam_corners", "ilcc2_read_lidar_corners", "ilcc2_read_camera_yaml",
 ]
 
 
@@ -46,6 +49,11 @@ class Diag(C.Structure):
         ("r_low", C.c_double), ("r_high", C.c_double), ("gray", C.c_double * 2),
         ("theta_t", (C.c_double * 3) * 2), ("cost", C.c_double * 2), ("cost_a", C.c_double * 2),
     ]
+
+
+class PnpSummary(C.Structure):
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double), ("iterations", C.c_int32),
+                ("termination", C.c_int32), ("n_evals", C.c_int32), ("n_pairs", C.c_int32)]
 
 
 _lib = None
@@ -88,5 +96,31 @@ def load() -> C.CDLL:
     L.ilcc2_save_corners2txt.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
     L.ilcc2_shard_range.restype = None
     L.ilcc2_shard_range.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.ilcc2_pnp_create.restype = C.c_int
+    L.ilcc2_pnp_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.ilcc2_pnp_destroy.restype = C.c_int
+    L.ilcc2_pnp_destroy.argtypes = [C.c_void_p]
+    L.ilcc2_pnp_last_error.restype = C.c_char_p
+    L.ilcc2_pnp_last_error.argtypes = [C.c_void_p]
+    L.ilcc2_pnp_launch_count.restype = C.c_int64
+    L.ilcc2_pnp_launch_count.argtypes = [C.c_void_p]
+    L.ilcc2_axis_roughly.restype = C.c_int
+    L.ilcc2_axis_roughly.argtypes = [C.c_char_p, C.c_void_p]
+    L.ilcc2_pnp_order_corners.restype = C.c_int
+    L.ilcc2_pnp_order_corners.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.ilcc2_pnp_solve.restype = C.c_int
+    L.ilcc2_pnp_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double,
+                                  C.c_int, C.c_void_p, C.c_void_p, C.POINTER(PnpSummary), C.c_int, C.c_void_p]
+    L.ilcc2_compose_extrinsic.restype = C.c_int
+    L.ilcc2_compose_extrinsic.argtypes = [C.c_void_p] * 4
+    L.ilcc2_extrinsic2bin.restype = C.c_int
+    L.ilcc2_extrinsic2bin.argtypes = [C.c_char_p, C.c_void_p]
+    L.ilcc2_read_cam_corners.restype = C.c_int
+    L.ilcc2_read_cam_corners.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.ilcc2_read_lidar_corners.restype = C.c_int
+    L.ilcc2_read_lidar_corners.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
+    L.ilcc2_read_camera_yaml.restype = C.c_int
+    L.ilcc2_read_camera_yaml.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L
     return L

@@ -301,3 +301,142 @@ class LidarCornersEst:
         self.m_cloud_corners = self._corners.copy()
         corners.extend([tuple(float(v) for v in c) for c in self._corners])
         return True
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# What follows the corner path (calib_lidar_cam.cpp:101-165): corner ordering + LiDAR->camera PnP, on the GPU.
+# ---------------------------------------------------------------------------------------------------------------
+def axis_roughly(camera_name: str) -> np.ndarray:
+    """get_lidar2cam_axis_roughly (calib_lidar_cam.cpp:50-70) as a row-major 4x4."""
+    T = np.zeros((4, 4))
+    if _lib.load().ilcc2_axis_roughly(camera_name.encode(), T.ctypes.data) != 0:
+        raise Ilcc2Error(f"unknown camera name {camera_name!r}")
+    return T
+
+
+def compose_extrinsic(r, t, T_axis) -> np.ndarray:
+    r, t, T_axis = (np.ascontiguousarray(a, np.float64) for a in (r, t, T_axis))
+    T = np.zeros((4, 4))
+    _lib.load().ilcc2_compose_extrinsic(r.ctypes.data, t.ctypes.data, T_axis.ctypes.data, T.ctypes.data)
+    return T
+
+
+def extrinsic2bin(path: str, T: np.ndarray):
+    T = np.ascontiguousarray(T, np.float64)
+    if _lib.load().ilcc2_extrinsic2bin(path.encode(), T.ctypes.data) != 0:
+        raise Ilcc2Error(f"can not write {path}")
+
+
+def read_cam_corners(path: str, num: int, board_h: int) -> np.ndarray:
+    out = np.zeros((4 * num, 2))
+    n = _lib.load().ilcc2_read_cam_corners(path.encode(), num, board_h, out.ctypes.data, out.shape[0])
+    if n < 0:
+        raise Ilcc2Error(f"can not read {path}")
+    return out[:n].copy()
+
+
+def read_lidar_corners(path: str, num: int) -> np.ndarray:
+    out = np.zeros((num, 3))
+    n = _lib.load().ilcc2_read_lidar_corners(path.encode(), num, out.ctypes.data)
+    if n < 0:
+        raise Ilcc2Error(f"can not read {path}")
+    return out[:n].copy()
+
+
+def read_camera_yaml(path: str):
+    K = np.zeros((3, 3))
+    cx, cy = C.c_int(0), C.c_int(0)
+    if _lib.load().ilcc2_read_camera_yaml(path.encode(), K.ctypes.data, C.byref(cx), C.byref(cy)) != 0:
+        raise Ilcc2Error(f"can not read K from {path}")
+    return K, cx.value, cy.value
+
+
+class PnpSolver:
+    """ilcc2_pnp_* : check_order_lidar / check_order_cam for a batch of frames and Optimization::solvePose3d2dError,
+    both on the GPU (csrc/ilcc2_pnp.cu)."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        rc = self._L.ilcc2_pnp_create(device, C.byref(self._h))
+        if rc != 0:
+            raise Ilcc2Error(f"ilcc2_pnp_create failed ({rc}): {self._L.ilcc2_pnp_last_error(None).decode()}")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.ilcc2_pnp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise Ilcc2Error(f"ilcc2 pnp error {rc}: {self._L.ilcc2_pnp_last_error(self._h).decode()}")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.ilcc2_pnp_launch_count(self._h))
+
+    def order_corners(self, lidar_corners, T_axis, board_w: int, board_h: int, status=None, cam_corners=None):
+        """numpy host arrays or torch CUDA tensors. Returns (pts3 (F*nc,3) f64, pts2 (F*nc,2) f64 | None, valid (F*nc,) u8)."""
+        T_axis = np.ascontiguousarray(T_axis, np.float64)
+        nc = board_w * board_h
+        if _is_torch(lidar_corners):
+            import torch
+            lc = lidar_corners.contiguous()
+            F = lc.shape[0]
+            assert lc.dtype == torch.float32 and lc.shape[1] == nc
+            p3 = torch.empty((F * nc, 3), dtype=torch.float64, device=lc.device)
+            p2 = torch.empty((F * nc, 2), dtype=torch.float64, device=lc.device) if cam_corners is not None else None
+            va = torch.empty((F * nc,), dtype=torch.uint8, device=lc.device)
+            cc = cam_corners.contiguous() if cam_corners is not None else None
+            stt = status.contiguous() if status is not None else None
+            stream = torch.cuda.current_stream(lc.device).cuda_stream
+            self._check(self._L.ilcc2_pnp_order_corners(
+                self._h, lc.data_ptr(), stt.data_ptr() if stt is not None else None,
+                cc.data_ptr() if cc is not None else None, F, board_w, board_h, T_axis.ctypes.data, p3.data_ptr(),
+                p2.data_ptr() if p2 is not None else None, va.data_ptr(), MEM_DEVICE, stream))
+            return p3, p2, va
+        lc = np.ascontiguousarray(lidar_corners, np.float32)
+        F = lc.shape[0]
+        assert lc.shape[1:] == (nc, 3)
+        p3 = np.empty((F * nc, 3))
+        cc = np.ascontiguousarray(cam_corners, np.float64) if cam_corners is not None else None
+        p2 = np.empty((F * nc, 2)) if cc is not None else None
+        va = np.empty((F * nc,), np.uint8)
+        stt = np.ascontiguousarray(status, np.int32) if status is not None else None
+        self._check(self._L.ilcc2_pnp_order_corners(
+            self._h, lc.ctypes.data, stt.ctypes.data if stt is not None else None,
+            cc.ctypes.data if cc is not None else None, F, board_w, board_h, T_axis.ctypes.data, p3.ctypes.data,
+            p2.ctypes.data if p2 is not None else None, va.ctypes.data, MEM_HOST, None))
+        return p3, p2, va
+
+    def solve(self, pts3, pts2, camera, r0=(0.0, 0.0, 0.0), t0=(0.0, 0.0, 0.0), valid=None, huber=0.1,
+              max_iterations=50):
+        """Optimization::solvePose3d2dError. Returns (r, t, summary dict)."""
+        camera = np.ascontiguousarray(camera, np.float64)
+        r, t = np.array(r0, np.float64), np.array(t0, np.float64)
+        sm = _lib.PnpSummary()
+        if _is_torch(pts3):
+            import torch
+            p3, p2 = pts3.contiguous(), pts2.contiguous()
+            assert p3.dtype == torch.float64 and p2.dtype == torch.float64
+            v = valid.contiguous() if valid is not None else None
+            stream = torch.cuda.current_stream(p3.device).cuda_stream
+            self._check(self._L.ilcc2_pnp_solve(self._h, p3.data_ptr(), p2.data_ptr(),
+                                                v.data_ptr() if v is not None else None, p3.shape[0],
+                                                camera.ctypes.data, huber, max_iterations, r.ctypes.data,
+                                                t.ctypes.data, C.byref(sm), MEM_DEVICE, stream))
+        else:
+            p3, p2 = np.ascontiguousarray(pts3, np.float64), np.ascontiguousarray(pts2, np.float64)
+            v = np.ascontiguousarray(valid, np.uint8) if valid is not None else None
+            self._check(self._L.ilcc2_pnp_solve(self._h, p3.ctypes.data, p2.ctypes.data,
+                                                v.ctypes.data if v is not None else None, p3.shape[0],
+                                                camera.ctypes.data, huber, max_iterations, r.ctypes.data,
+                                                t.ctypes.data, C.byref(sm), MEM_HOST, None))
+        return r, t, {k: getattr(sm, k) for k, _ in _lib.PnpSummary._fields_}

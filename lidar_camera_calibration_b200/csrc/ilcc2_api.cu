@@ -253,8 +253,9 @@ int ilcc2_create(const ilcc2_params* params, int device, int max_frames, int max
   A(dev_alloc(h, &w.opt_white, F * R));
   A(dev_alloc(h, &w.opt_count, F));
   A(dev_alloc(h, &w.fit_order, F));
+  A(dev_alloc(h, &w.fit_done, F));
   w.num_sms = prop.multiProcessorCount;
-  w.fit_stride = (h->cap + 31) / 32 + (long long)kFitWarps * h->cap;
+  w.fit_stride = (h->cap + 31) / 32 + 2ll * kFitTeam * h->cap;
   A(dev_alloc(h, &w.fit_scratch, h->cap > kFitBitsCap ? F * (size_t)w.fit_stride : 1));
   A(dev_alloc(h, &h->d_clicks, F * 3));
   A(dev_alloc(h, &h->d_flags, F));

@@ -39,8 +39,15 @@ constexpr int kPlaneThreads = 128;    // K3/K4 CTA size == canonical reduction w
 #ifndef FIT_TEAM
 #define FIT_TEAM 2
 #endif
+#ifndef FIT_SPLIT
+#define FIT_SPLIT 1
+#endif
 constexpr int kFitTeam = FIT_TEAM;    // K5: warps that share one solve (one colour hypothesis of one frame)
-constexpr int kFitWarps = 2 * kFitTeam;  // K5: team 0 = hypothesis topleftWhite=false, team 1 = true
+// FIT_SPLIT=1: one CTA per (frame, colour hypothesis) -- the CTA of the cheaper hypothesis frees its registers as soon
+// as it is done; the CTA that finishes second picks the lower cost and emits the corners.  FIT_SPLIT=0: both
+// hypotheses in one CTA (team 0 = topleftWhite=false, team 1 = true).
+constexpr int kFitTeamsPerCta = FIT_SPLIT ? 1 : 2;
+constexpr int kFitWarps = kFitTeamsPerCta * kFitTeam;
 constexpr int kFitThreads = 32 * kFitWarps;
 constexpr int kFitListCap = 3200;     // K5: per-warp candidate list buffer in shared memory = chunk length (multiple of 32)
 constexpr int kFitBitsCap = 8192;      // K5: colour bits kept in shared memory; larger frames take the global-memory path
@@ -77,6 +84,7 @@ struct Workspace {
   uint8_t* opt_white;          // [F][R]
   int* opt_count;              // [F]
   int* fit_order;              // [F] block index -> frame for K5 (work-balanced order)
+  int* fit_done;               // [F] K5 with one CTA per hypothesis: CTAs of the frame that have finished
   int num_sms;
   uint32_t* fit_scratch;       // [F][fit_stride] K5 global-memory path: colour bits + two index lists
   long long fit_stride;

@@ -1780,7 +1780,12 @@ __device__ __forceinline__ void team_sum(double (&v)[NQ], double* slots /* [2][k
 #pragma unroll
     for (int q = 0; q < NQ; ++q) buf[wt * 9 + q] = v[q];
   }
-  asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(32 * kFitTeam) : "memory");
+  // immediate barrier ids: with a register id ptxas reserves all 16 named barriers for the CTA, and the barrier
+  // pool of the SM then caps the number of resident CTAs
+  if (team == 0)
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kFitTeam) : "memory");
+  else
+    asm volatile("bar.sync 2, %0;" ::"n"(32 * kFitTeam) : "memory");
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     double t = buf[q];
@@ -1981,7 +1986,7 @@ __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, 
 #ifdef FIT_TIMING
   t_scalar += clock64() - t0;
   if (lane == 0) {
-    if ((threadIdx.x >> 5) == 0) {
+    if ((threadIdx.x >> 5) == 0 && (!FIT_SPLIT || (blockIdx.x & 1) == 0)) {
       atomicAdd(&Fp->timing[0], (float)t_cls * 1e-3f);
       atomicAdd(&Fp->timing[1], (float)(t_eval - t_cls) * 1e-3f);
       atomicAdd(&Fp->timing[2], (float)t_jac * 1e-3f);
@@ -2019,7 +2024,10 @@ __global__ void __launch_bounds__(1024) fit_order_kernel(const Workspace w, int 
     const int n = (w.diag[f].status == ILCC2_OK) ? w.opt_count[f] : 0;
     return NB - 1 - min(n >> 5, NB - 1);  // descending size
   };
-  for (int f = tid; f < F; f += blockDim.x) atomicAdd(&s_hist[bucket(f)], 1);
+  for (int f = tid; f < F; f += blockDim.x) {
+    atomicAdd(&s_hist[bucket(f)], 1);
+    w.fit_done[base + f] = 0;
+  }
   __syncthreads();
   if (tid == 0) {
     int acc = 0;
@@ -2050,32 +2058,37 @@ __global__ void __launch_bounds__(1024) fit_order_kernel(const Workspace w, int 
 //               frames above kFitListCap points are evaluated in chunks of kFitListCap)
 // SMEM = false: larger frames; same code on global-memory scratch.  Both are launched; each skips the other's frames.
 #ifndef FIT_MINB
-#define FIT_MINB (kFitTeam == 1 ? 7 : 8 / kFitTeam)
+#define FIT_MINB (512 / kFitThreads > 7 && kFitThreads == 64 && !FIT_SPLIT ? 7 : 512 / kFitThreads)
 #endif
 template <bool SMEM>
-__global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : (kFitTeam == 1 ? 4 : 2)) board_fit_kernel(const Workspace w, const DevParams p) {
+__global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 256 / kFitThreads) board_fit_kernel(const Workspace w, const DevParams p) {
   using IdxT = typename std::conditional<SMEM, uint16_t, uint32_t>::type;
   extern __shared__ unsigned char fit_sm[];
   __shared__ double s_x[2][3];
   __shared__ double s_cost[2];
   __shared__ float s_ext[kFitWarps][2];
-  __shared__ double s_red[2][2 * kFitTeam * 9];  // team_sum slots: [team][parity][warp of team][9]
+  __shared__ double s_red[kFitTeamsPerCta][2 * kFitTeam * 9];  // team_sum slots: [team][parity][warp of team][9]
+  __shared__ int s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int f = w.fit_order[w.frame_base + blockIdx.x];  // big frames first, dealt to the SMs in snake order (fit_order_kernel)
+  const int fblock = FIT_SPLIT ? (blockIdx.x >> 1) : blockIdx.x;
+  const int hyp_cta = FIT_SPLIT ? (blockIdx.x & 1) : 0;
+  const int f = w.fit_order[w.frame_base + fblock];  // big frames first (fit_order_kernel)
   ilcc2_diag* d = w.diag + f;
   float* corners = w.corners + (size_t)f * p.ncorners * 3;
   const int st = d->status;
   const int n = w.opt_count[f];
   if (st == ILCC2_OK && (n <= kFitBitsCap) != SMEM) return;  // the other instantiation owns this frame
   if (st != ILCC2_OK) {
-    if (SMEM) {
+    if (SMEM && hyp_cta == 0) {
       for (int i = tid; i < p.ncorners * 3; i += kFitThreads) corners[i] = NAN;
       if (tid == 0) w.status[f] = st;
     }
     return;
   }
   const unsigned flags = w.flags ? (unsigned)w.flags[f] : w.default_flags;
+  const bool autom = (flags & ILCC2_FLAG_AUTO) != 0;
+  if (FIT_SPLIT && !autom && hyp_cta == 1) return;  // manual mode: one CTA runs the requested hypotheses in sequence
   const float2* gyz = w.opt_yz + (size_t)f * w.cap;
   const uint8_t* gwh = w.opt_white + (size_t)f * w.cap;
   FitPts<IdxT> F;
@@ -2094,7 +2107,7 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : (kFitTeam == 1 
     uint32_t* g = w.fit_scratch + (size_t)f * w.fit_stride;
     wbits = g;
     F.yz = gyz;
-    F.list = reinterpret_cast<IdxT*>(g + (w.cap + 31) / 32 + (size_t)warp * w.cap);
+    F.list = reinterpret_cast<IdxT*>(g + (w.cap + 31) / 32 + (size_t)(hyp_cta * kFitTeam + warp) * w.cap);
     F.list_cap = w.cap;
   }
   float ymax = 0.f, zmax = 0.f;
@@ -2119,12 +2132,11 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : (kFitTeam == 1 
   F.wbits = wbits;
   F.timing = d->plane;
 #ifdef FIT_TIMING
-  if (tid < 4) F.timing[tid] = 0.f;
+  if (tid < 4 && hyp_cta == 0) F.timing[tid] = 0.f;
 #endif
   if (tid < 2) s_cost[tid] = 0.0;
   __syncthreads();
 
-  const bool autom = (flags & ILCC2_FLAG_AUTO) != 0;
   VbModel M;
   M.Wd = (double)p.W;
   M.Hd = (double)p.H;
@@ -2142,7 +2154,8 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : (kFitTeam == 1 
     }
     M.ymax_zmax = ym + zm;
   }
-  const int team = warp / kFitTeam, wt = warp % kFitTeam;
+  const int team_local = warp / kFitTeam, wt = warp % kFitTeam;
+  const int team = FIT_SPLIT ? hyp_cta : team_local;  // colour hypothesis this team solves in auto mode
   if (autom || team == 0) {
     const int h_first = autom ? team : 0;
     const int h_last = autom ? team : ((flags & ILCC2_FLAG_TOPLEFT_WHITE) ? 1 : 0);
@@ -2152,9 +2165,9 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : (kFitTeam == 1 
       int evals = 0, it0 = 0, it1 = 0;
       double fc = 0.0;
       M.tlw = h;
-      const int term0 = solve_tr<IdxT>(&F, &M, 1, p.max_solver_iter, lane, x, &fc, &it0, &evals, s_red[team], &parity);  // useOutofBoard
+      const int term0 = solve_tr<IdxT>(&F, &M, 1, p.max_solver_iter, lane, x, &fc, &it0, &evals, s_red[team_local], &parity);  // useOutofBoard
       if (lane == 0 && wt == 0) d->cost_a[h] = fc;
-      const int term1 = solve_tr<IdxT>(&F, &M, 0, p.max_solver_iter, lane, x, &fc, &it1, &evals, s_red[team], &parity);  // then without
+      const int term1 = solve_tr<IdxT>(&F, &M, 0, p.max_solver_iter, lane, x, &fc, &it1, &evals, s_red[team_local], &parity);  // then without
       if (lane == 0 && wt == 0) {
         d->iters[h][0] = it0;
         d->iters[h][1] = it1;
@@ -2171,6 +2184,23 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : (kFitTeam == 1 
     }
   }
   __syncthreads();
+  if (FIT_SPLIT && autom) {
+    // the CTA of the other hypothesis publishes through diag; whichever CTA arrives second finishes the frame
+    if (tid == 0) {
+      __threadfence();
+      s_last = atomicAdd(&w.fit_done[f], 1);
+    }
+    __syncthreads();
+    if (s_last == 0) return;
+    __threadfence();
+    if (tid < 2) {
+      const int oh = 1 - hyp_cta;
+      volatile const double* vd = reinterpret_cast<volatile const double*>(d->theta_t[oh]);
+      if (tid == 0) s_cost[oh] = *reinterpret_cast<volatile const double*>(&d->cost[oh]);
+      for (int i = tid; i < 3; i += 2) s_x[oh][i] = vd[i];
+    }
+    __syncthreads();
+  }
   const int chosen = autom ? ((s_cost[1] < s_cost[0]) ? 1 : 0) : ((flags & ILCC2_FLAG_TOPLEFT_WHITE) ? 1 : 0);
   // getPCDcorners: lattice -> transOptim^-1 -> transPCA^-1, fp32
   int W = p.W, H = p.H;
@@ -2209,8 +2239,9 @@ size_t fit_smem_bytes() {
 
 void launch_board_fit(const Workspace& w, const DevParams& p, cudaStream_t s) {
   fit_order_kernel<<<1, 1024, 0, s>>>(w, w.num_sms);
-  board_fit_kernel<true><<<w.n_frames, kFitThreads, fit_smem_bytes(), s>>>(w, p);
-  if (w.cap > kFitBitsCap) board_fit_kernel<false><<<w.n_frames, kFitThreads, 0, s>>>(w, p);
+  const int grid = (FIT_SPLIT ? 2 : 1) * w.n_frames;
+  board_fit_kernel<true><<<grid, kFitThreads, fit_smem_bytes(), s>>>(w, p);
+  if (w.cap > kFitBitsCap) board_fit_kernel<false><<<grid, kFitThreads, 0, s>>>(w, p);
 }
 
 cudaError_t configure_kernels() {

@@ -49,3 +49,14 @@ def allgather_corners(corners, status, world_size: int, out_corners=None, out_st
     dist.all_gather_into_tensor(out_corners, corners.contiguous())
     dist.all_gather_into_tensor(out_status, status.contiguous())
     return out_corners, out_status
+
+
+def allgather_rows(x, world_size: int):
+    """Concatenation over ranks (rank order) of a tensor with the same shape on every rank."""
+    import torch
+    import torch.distributed as dist
+    if world_size == 1:
+        return x
+    out = torch.empty((world_size * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous())
+    return out

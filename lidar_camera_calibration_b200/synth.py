@@ -206,3 +206,32 @@ def corner_set_distance(a: np.ndarray, b: np.ndarray) -> float:
     """Order-free parity metric: max over corners of a of the distance to the nearest corner of b (and vice versa)."""
     d = np.linalg.norm(a[:, None, :].astype(np.float64) - b[None, :, :].astype(np.float64), axis=2)
     return float(max(d.min(1).max(), d.min(0).max()))
+
+
+# ---- synthetic camera side for BASELINE.json configs[4] (SURVEY.md 8(d) "Config 5") ----
+# Planted LiDAR->camera extrinsic = the reference's shipped ilcc2/config/pointgrey.bin (row-major 4x4) and the
+# intrinsics of ilcc2/config/pointgrey.yaml (fx, cx, fy, cy).
+PLANTED_EXTRINSIC = np.array([
+    [0.030776439680377833, -0.999522902318748, 0.0026035554356903844, -0.05487600789921265],
+    [-0.003282631634222143, -0.0027058505464300914, -0.9999909513102478, -0.0740006228856876],
+    [0.999520902778003, 0.030767614680488886, -0.003364341944407353, -0.08264568089777906],
+    [0.0, 0.0, 0.0, 1.0]])
+PLANTED_CAMERA = np.array([1061.37439737547, 980.706836288949, 1061.02435228316, 601.685030610243])
+
+
+def project_truth(gt: np.ndarray, scene: Scene = SCENE_VLP16, start: int = 0, noise_px: float = 0.5,
+                  base_seed: int = BASE_SEED) -> np.ndarray:
+    """Image corners (F, ncorn, 2) of the ground-truth 3-D corners under the planted extrinsic + N(0, noise_px),
+    laid out like the reference's camera corner files after read_cam_corners: rows along the short board side,
+    columns along the long one (the LiDAR lattice of getPCDcorners has the same shape; the reference's
+    check_order_lidar / check_order_cam remove the remaining flips)."""
+    b = scene.board
+    F = gt.shape[0]
+    q = gt.reshape(F, b.corners_long, b.corners_short, 3).transpose(0, 2, 1, 3).reshape(F, -1, 3)
+    q = q @ PLANTED_EXTRINSIC[:3, :3].T + PLANTED_EXTRINSIC[:3, 3]
+    fx, cx, fy, cy = PLANTED_CAMERA
+    uv = np.stack([fx * q[..., 0] / q[..., 2] + cx, fy * q[..., 1] / q[..., 2] + cy], -1)
+    for f in range(F):
+        rng = np.random.Generator(np.random.Philox(key=[base_seed ^ 0x5EED, start + f]))
+        uv[f] += rng.normal(0.0, noise_px, uv[f].shape)
+    return uv
