@@ -4,6 +4,7 @@
 // every compute entry point fails loudly when CUDA is unavailable.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -255,7 +256,7 @@ int ilcc2_create(const ilcc2_params* params, int device, int max_frames, int max
   A(dev_alloc(h, &w.fit_order, F));
   A(dev_alloc(h, &w.fit_done, F));
   w.num_sms = prop.multiProcessorCount;
-  w.fit_stride = (h->cap + 31) / 32 + 2ll * kFitTeam * h->cap;
+  w.fit_stride = (h->cap + 31) / 32 + 2ll * kFitGlobalTeam * h->cap;
   A(dev_alloc(h, &w.fit_scratch, h->cap > kFitBitsCap ? F * (size_t)w.fit_stride : 1));
   A(dev_alloc(h, &h->d_clicks, F * 3));
   A(dev_alloc(h, &h->d_flags, F));
@@ -422,12 +423,38 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
   // following chunks and the kernels of its neighbours (a small chunk leaves most SMs idle on its own: its run
   // time is the latency of its slowest frame).  Needs page-locked host memory to actually overlap.
   // Device buffers, profiling runs and ragged batches: one chunk on the caller's stream.
-  int chunk = n_frames;
+  // Chunk schedule: equal chunks of e2e_chunk_frames, except that the batch ENDS with two short chunks (3/4 and 1/4
+  // of a chunk).  After the last copy only the last chunk's kernels remain, and K5's run time is the latency of its
+  // slowest solve, which launch_board_fit shortens for small launches by putting more warps on each solve.
+  std::vector<int> cb, cn;  // first frame / frame count of every chunk
   if (mem_kind == ILCC2_MEM_HOST && !prof && !debug_sync && !frame_offsets && n_frames > h->e2e_chunk_frames) {
-    chunk = h->e2e_chunk_frames;
-    while ((n_frames + chunk - 1) / chunk > ilcc2_handle::kMaxChunks) chunk *= 2;
+    int C = h->e2e_chunk_frames;
+    while ((n_frames + C - 1) / C + 2 > ilcc2_handle::kMaxChunks) C *= 2;
+    const int tail1 = std::max(1, C / 4), tail2 = std::max(1, 3 * C / 4);
+    int body = n_frames - tail1 - tail2;
+    int f0 = 0;
+    if (body > 0) {
+      const int nb = (body + C - 1) / C;
+      for (int i = 0; i < nb; ++i) {  // spread the remainder over the body chunks
+        const int nf = body / nb + (i < body % nb ? 1 : 0);
+        cb.push_back(f0);
+        cn.push_back(nf);
+        f0 += nf;
+      }
+    }
+    for (int t : {tail2, tail1}) {
+      const int nf = std::min(t, n_frames - f0);
+      if (nf > 0) {
+        cb.push_back(f0);
+        cn.push_back(nf);
+        f0 += nf;
+      }
+    }
+  } else {
+    cb.push_back(0);
+    cn.push_back(n_frames);
   }
-  const int n_chunks = (n_frames + chunk - 1) / chunk;
+  const int n_chunks = (int)cb.size();
   if (mem_kind == ILCC2_MEM_HOST) {
     if (n_chunks == 1) {
       CU_TRY(h, cudaMemcpyAsync(h->d_points_stage, points, bytes, cudaMemcpyHostToDevice, s));
@@ -437,18 +464,17 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
       for (int i = 0; i < ilcc2_handle::kWorkStreams; ++i) CU_TRY(h, cudaStreamWaitEvent(h->work_stream[i], h->ev_start, 0));
       const size_t frame_bytes = (size_t)points_per_frame * point_step;
       for (int c = 0; c < n_chunks; ++c) {
-        const int f0 = c * chunk, nf = (f0 + chunk <= n_frames) ? chunk : n_frames - f0;
-        CU_TRY(h, cudaMemcpyAsync(h->d_points_stage + (size_t)f0 * frame_bytes,
-                                  static_cast<const unsigned char*>(points) + (size_t)f0 * frame_bytes,
-                                  (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CU_TRY(h, cudaMemcpyAsync(h->d_points_stage + (size_t)cb[c] * frame_bytes,
+                                  static_cast<const unsigned char*>(points) + (size_t)cb[c] * frame_bytes,
+                                  (size_t)cn[c] * frame_bytes, cudaMemcpyHostToDevice, h->copy_stream));
         CU_TRY(h, cudaEventRecord(h->ev_copied[c], h->copy_stream));
       }
     }
   }
   CU_TRY(h, stage_done(0));
   for (int c = 0; c < n_chunks; ++c) {
-    w.frame_base = c * chunk;
-    w.n_frames = (w.frame_base + chunk <= n_frames) ? chunk : n_frames - w.frame_base;
+    w.frame_base = cb[c];
+    w.n_frames = cn[c];
     cudaStream_t cs = n_chunks > 1 ? h->work_stream[c % ilcc2_handle::kWorkStreams] : s;
     if (n_chunks > 1) CU_TRY(h, cudaStreamWaitEvent(cs, h->ev_copied[c], 0));
     launch_roi_filter(w, h->dp, cs);

@@ -36,20 +36,19 @@ constexpr int kClusterSmemSlots = 8192;
 constexpr int kClusterBitmapRows = 2944; // K2: occupancy bitmap rows (ncy*ncz) that fit the shared-memory layout
 constexpr int kClusterQueue = 160;       // K2: per-warp queue of (cell, neighbour) pairs: 32 lanes x 5 dx
 constexpr int kPlaneThreads = 128;    // K3/K4 CTA size == canonical reduction width of their double sums
-#ifndef FIT_TEAM
-#define FIT_TEAM 2
+// K5: one CTA per (frame, colour hypothesis); the CTA is a team of T warps that share the solve.  T is chosen per
+// launch so that the batch fills the machine (launch_board_fit): 2 for large batches, 4 / 8 for small ones, where the
+// latency of one solve is what the caller waits for.  The CTA that finishes second picks the lower cost and emits
+// the corners.
+constexpr int kFitMaxTeam = 8;
+constexpr int kFitGlobalTeam = 2;     // team size of the global-memory instantiation (frames above kFitBitsCap points)
+#ifndef FIT_TEAM_CAP
+#define FIT_TEAM_CAP 3328
 #endif
-#ifndef FIT_SPLIT
-#define FIT_SPLIT 1
-#endif
-constexpr int kFitTeam = FIT_TEAM;    // K5: warps that share one solve (one colour hypothesis of one frame)
-// FIT_SPLIT=1: one CTA per (frame, colour hypothesis) -- the CTA of the cheaper hypothesis frees its registers as soon
-// as it is done; the CTA that finishes second picks the lower cost and emits the corners.  FIT_SPLIT=0: both
-// hypotheses in one CTA (team 0 = topleftWhite=false, team 1 = true).
-constexpr int kFitTeamsPerCta = FIT_SPLIT ? 1 : 2;
-constexpr int kFitWarps = kFitTeamsPerCta * kFitTeam;
-constexpr int kFitThreads = 32 * kFitWarps;
-constexpr int kFitListCap = 3200;     // K5: per-warp candidate list buffer in shared memory = chunk length (multiple of 32)
+// K5: points per chunk of a solve (multiple of 32 * kFitMaxTeam).  Each of the T warps of a team owns a candidate list of
+// kFitTeamCap / T 16-bit entries in shared memory, so the footprint (6.5 KB + 1 KB of colour bits per CTA) does not
+// depend on T and most of the SM's 256 KB stay L1 for the points.  Frames with more points are evaluated in chunks.
+constexpr int kFitTeamCap = FIT_TEAM_CAP;
 constexpr int kFitBitsCap = 8192;      // K5: colour bits kept in shared memory; larger frames take the global-memory path
 constexpr int kRndTable = 8192;       // PCL RANSAC draw table length
 
@@ -102,6 +101,7 @@ void launch_pca_gray(const Workspace& w, const DevParams& p, cudaStream_t s);
 void launch_board_fit(const Workspace& w, const DevParams& p, cudaStream_t s);
 cudaError_t configure_kernels();
 size_t cluster_smem_bytes();
-size_t fit_smem_bytes();
+size_t fit_smem_bytes(int team);
+int fit_team_size(int frames, int num_sms);
 
 }  // namespace ilcc2

@@ -1408,7 +1408,7 @@ __device__ __forceinline__ void classify_pass(const float2* __restrict__ yz, con
   int c1 = 0, c2 = 0;
   const unsigned lt = (1u << lane) - 1u;
 #ifndef CLS_UNROLL
-#define CLS_UNROLL 4
+#define CLS_UNROLL 2
 #endif
   constexpr int U = CLS_UNROLL;  // independent points per lane per iteration: the warp is latency-bound, not issue-bound
   for (int base = k0; base < k1; base += 32 * U) {
@@ -1540,6 +1540,23 @@ struct Dogleg {
   int sub1d;
   double U[3][2], sub_g[2], sub_B[3];
   double step_norm;
+};
+
+// Per-warp scratch of the scalar solver, kept in SHARED memory: the out-of-line dogleg routines take these by
+// reference, which would otherwise put them on the local-memory stack -- 128 B of L1 per 4-byte slot and warp, i.e.
+// ~8 KB per warp that competes with the frame's points for L1 (ncu: long-scoreboard stalls in the scalar code and
+// 85 MB of local-memory write-back per launch).  All lanes of a warp hold identical values, so they all store the
+// same data to the same address.
+#ifndef FIT_WS_LOCAL
+#define FIT_WS_SHARED 1
+#endif
+struct ScalarWs {
+  Dogleg S;
+  double Hs[6], gs[3], step[3];
+  // iterate / bookkeeping of solve_tr: only touched between evaluations, so keeping them here frees ~50 registers
+  // inside the classification and list loops
+  double xc[3], cand[3], g[3], H[6], scale[3], xbest[3];
+  double x_cost, xnorm, best_cost, model_change, gmax;
 };
 
 __device__ __forceinline__ double norm3(const double v[3]) { return dsqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
@@ -1767,30 +1784,25 @@ __device__ __noinline__ bool dogleg_compute_step(Dogleg& S, const double Hs[6], 
 
 enum { TERM_MAX_ITER = 0, TERM_GRADIENT = 1, TERM_PARAMETER = 2, TERM_FUNCTION = 3, TERM_MIN_RADIUS = 4, TERM_INVALID = 5 };
 
-// Sum of per-warp totals over the kFitTeam warps that share a solve.  Every warp of the team ends up with the
-// bit-identical total (fixed order: warp 0 of the team first), so the scalar solver can run redundantly on all of
-// them without any further exchange.  One named barrier per call; the slots are double-buffered (`parity`), which
-// is enough because a warp cannot run two reductions ahead of its team mates.
-template <int NQ>
-__device__ __forceinline__ void team_sum(double (&v)[NQ], double* slots /* [2][kFitTeam][9] of this team */, int team,
-                                         int wt, int lane, int& parity) {
-  if (kFitTeam == 1) return;
-  double* buf = slots + parity * (kFitTeam * 9);
+// Sum of per-warp totals over the T warps that share a solve (= the CTA).  Every warp ends up with the bit-identical
+// total (fixed order: warp 0 first), so the scalar solver can run redundantly on all of them without any further
+// exchange.  One barrier per call; the slots are double-buffered (`parity`), which is enough because a warp cannot
+// run two reductions ahead of its team mates.  (An immediate barrier id: with a register id ptxas reserves all 16
+// named barriers for the CTA, and the barrier pool of the SM then caps the number of resident CTAs.)
+template <int NQ, int T>
+__device__ __forceinline__ void team_sum(double (&v)[NQ], double* slots /* [2][T][9] */, int wt, int lane, int& parity) {
+  if (T == 1) return;
+  double* buf = slots + parity * (T * 9);
   if (lane == 0) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q) buf[wt * 9 + q] = v[q];
   }
-  // immediate barrier ids: with a register id ptxas reserves all 16 named barriers for the CTA, and the barrier
-  // pool of the SM then caps the number of resident CTAs
-  if (team == 0)
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * kFitTeam) : "memory");
-  else
-    asm volatile("bar.sync 2, %0;" ::"n"(32 * kFitTeam) : "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * T) : "memory");
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     double t = buf[q];
 #pragma unroll
-    for (int w = 1; w < kFitTeam; ++w) t += buf[w * 9 + q];
+    for (int w = 1; w < T; ++w) t += buf[w * 9 + q];
     v[q] = t;
   }
   parity ^= 1;
@@ -1801,10 +1813,17 @@ __device__ __forceinline__ void team_sum(double (&v)[NQ], double* slots /* [2][k
 // "accepted"), so that the classification / evaluation code exists exactly once in the kernel image.
 // Rejected Gauss-Newton steps that would be recomputed identically (radius still above |GN|) are fast-forwarded:
 // iteration counter and radius advance exactly as if the same candidate had been evaluated and rejected again.
-template <typename IdxT>
-__device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, int oob_i, int max_iter, int lane,
+// Inlined into its single call site (the phase loop of board_fit_kernel): the model constants then come straight
+// from the kernel parameters and nothing is spilled around the call (ncu/ptxas: 216 B -> 0 B of spills, -8 % time).
+#ifdef FIT_SOLVE_NOINLINE
+#define FIT_SOLVE_ATTR __noinline__
+#else
+#define FIT_SOLVE_ATTR __forceinline__
+#endif
+template <typename IdxT, int T>
+__device__ FIT_SOLVE_ATTR int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, int oob_i, int max_iter, int lane,
                                      double* x, double* final_cost, int* iters_out, int* n_evals_io, double* slots,
-                                     int* parity_io) {
+                                     int* parity_io, ScalarWs* ws_shared) {
   const float2* __restrict__ yz = Fp->yz;
   const uint32_t* wbits = Fp->wbits;
   IdxT* list = Fp->list;
@@ -1814,21 +1833,39 @@ __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, 
     // LDS/STS with 32-bit addresses instead of generic loads/stores
     extern __shared__ unsigned char fit_sm[];
     wbits = reinterpret_cast<const uint32_t*>(fit_sm);
-    list = reinterpret_cast<IdxT*>(fit_sm + sizeof(uint32_t) * (kFitBitsCap / 32)) + (size_t)(threadIdx.x >> 5) * kFitListCap;
-    list_cap = kFitListCap;
+    list = reinterpret_cast<IdxT*>(fit_sm + sizeof(uint32_t) * (kFitBitsCap / 32)) + (size_t)(threadIdx.x >> 5) * (kFitTeamCap / T);
+    list_cap = kFitTeamCap / T;
   }
   const int n = Fp->n;
   const VbModel M = *Mp;
   const bool oob = oob_i != 0;
-  const int team = (threadIdx.x >> 5) / kFitTeam, wt = (threadIdx.x >> 5) % kFitTeam;
+  const int wt = threadIdx.x >> 5;  // warp of the team
   int parity = *parity_io;
-  const int team_cap = kFitTeam * list_cap;  // points per chunk: each warp of the team classifies / evaluates its share
+  const int team_cap = T * list_cap;  // points per chunk: each warp of the team classifies / evaluates its share
 
+#ifdef FIT_WS_SHARED
+  ScalarWs& ws = *ws_shared;
+#else
+  ScalarWs ws_local;
+  ScalarWs& ws = ws_local;
+#endif
+#if defined(FIT_WS_SHARED) && !defined(FIT_WS_SMALL)
+  double *xc = ws.xc, *cand = ws.cand, *g = ws.g, *H = ws.H, *scale = ws.scale, *xbest = ws.xbest;
+  double &x_cost = ws.x_cost, &xnorm = ws.xnorm, &best_cost = ws.best_cost, &model_change = ws.model_change, &gmax = ws.gmax;
+  for (int i = 0; i < 3; ++i) {
+    xc[i] = cand[i] = xbest[i] = x[i];
+    g[i] = 0.0;
+    scale[i] = 1.0;
+  }
+  for (int i = 0; i < 6; ++i) H[i] = 0.0;
+  x_cost = xnorm = best_cost = model_change = gmax = 0.0;
+#else
   double xc[3] = {x[0], x[1], x[2]}, cand[3] = {x[0], x[1], x[2]};
   double g[3] = {0, 0, 0}, H[6] = {0, 0, 0, 0, 0, 0}, scale[3] = {1, 1, 1};
   double x_cost = 0.0, xnorm = 0.0, best_cost = 0.0, xbest[3] = {x[0], x[1], x[2]};
   double model_change = 0.0, gmax = 0.0;
-  Dogleg S;
+#endif
+  Dogleg& S = ws.S;
   S.radius = 1e4;
   S.mu = 1e-8;
   S.reuse = 0;
@@ -1857,7 +1894,7 @@ __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, 
 #endif
       // this warp's share of the chunk: a 32-aligned contiguous piece (may be empty)
       const int k1 = min(k0 + team_cap, n);
-      const int piece = (((k1 - k0) + kFitTeam - 1) / kFitTeam + 31) & ~31;
+      const int piece = (((k1 - k0) + T - 1) / T + 31) & ~31;
       const int ka = min(k0 + wt * piece, k1), kb = min(ka + piece, k1);
       classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, cand[1], cand[2], lane, ka, kb, n1, n2);
 #ifdef FIT_TIMING
@@ -1867,7 +1904,7 @@ __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, 
       if (k0 + team_cap < n) __syncwarp();
     }
     double cc1[1] = {warp_butterfly(a[0])};
-    team_sum<1>(cc1, slots, team, wt, lane, parity);
+    team_sum<1, T>(cc1, slots, wt, lane, parity);
     const double cc = cc1[0];
     n_evals++;
 #ifdef FIT_TIMING
@@ -1897,7 +1934,7 @@ __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, 
         for (int k0 = 0; k0 < n; k0 += team_cap) {
           __syncwarp();
           const int k1 = min(k0 + team_cap, n);
-          const int piece = (((k1 - k0) + kFitTeam - 1) / kFitTeam + 31) & ~31;
+          const int piece = (((k1 - k0) + T - 1) / T + 31) & ~31;
           const int ka = min(k0 + wt * piece, k1), kb = min(ka + piece, k1);
           classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, xc[1], xc[2], lane, ka, kb, n1, n2);
           list_pass<IdxT>(yz, wbits, list, list_cap, M, oob, true, cs, sn, xc[1], xc[2], lane, n1, n2, a);
@@ -1905,7 +1942,7 @@ __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, 
       }
 #pragma unroll
       for (int q = 0; q < 9; ++q) a[q] = warp_butterfly(a[q]);
-      team_sum<9>(a, slots, team, wt, lane, parity);
+      team_sum<9, T>(a, slots, wt, lane, parity);
       g[0] = a[0];
       g[1] = a[1];
       g[2] = a[2];
@@ -1948,13 +1985,15 @@ __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, 
     first = false;
     // ---- next trust-region step (loops over invalid steps) ----
     bool stop = false;
-    double step[3] = {0, 0, 0};
+    double* step = ws.step;
+    step[0] = step[1] = step[2] = 0.0;
     for (;;) {
       if (iter >= max_iter) { term = TERM_MAX_ITER; stop = true; break; }
       if (succ && gmax <= 1e-10) { term = TERM_GRADIENT; stop = true; break; }
       if (S.radius <= 1e-32) { term = TERM_MIN_RADIUS; stop = true; break; }
       iter++;
-      double Hs[6], gs[3];
+      double* Hs = ws.Hs;
+      double* gs = ws.gs;
       Hs[0] = H[0] * scale[0] * scale[0];
       Hs[1] = H[1] * scale[0] * scale[1];
       Hs[2] = H[2] * scale[0] * scale[2];
@@ -1986,7 +2025,7 @@ __device__ __noinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, 
 #ifdef FIT_TIMING
   t_scalar += clock64() - t0;
   if (lane == 0) {
-    if ((threadIdx.x >> 5) == 0 && (!FIT_SPLIT || (blockIdx.x & 1) == 0)) {
+    if ((threadIdx.x >> 5) == 0 && (blockIdx.x & 1) == 0) {
       atomicAdd(&Fp->timing[0], (float)t_cls * 1e-3f);
       atomicAdd(&Fp->timing[1], (float)(t_eval - t_cls) * 1e-3f);
       atomicAdd(&Fp->timing[2], (float)t_jac * 1e-3f);
@@ -2055,24 +2094,26 @@ __global__ void __launch_bounds__(1024) fit_order_kernel(const Workspace w, int 
 }
 
 // SMEM = true : frames with at most kFitBitsCap optimiser points (16-bit candidate lists + colour bits in shared memory;
-//               frames above kFitListCap points are evaluated in chunks of kFitListCap)
+//               frames above kFitTeamCap points are evaluated in chunks of kFitTeamCap)
 // SMEM = false: larger frames; same code on global-memory scratch.  Both are launched; each skips the other's frames.
-#ifndef FIT_MINB
-#define FIT_MINB (512 / kFitThreads > 7 && kFitThreads == 64 && !FIT_SPLIT ? 7 : 512 / kFitThreads)
+#ifndef FIT_WARPS_PER_SM
+#define FIT_WARPS_PER_SM 16
 #endif
-template <bool SMEM>
-__global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 256 / kFitThreads) board_fit_kernel(const Workspace w, const DevParams p) {
+template <bool SMEM, int T>
+__global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) board_fit_kernel(const Workspace w, const DevParams p) {
   using IdxT = typename std::conditional<SMEM, uint16_t, uint32_t>::type;
+  constexpr int kThreads = 32 * T;
   extern __shared__ unsigned char fit_sm[];
   __shared__ double s_x[2][3];
   __shared__ double s_cost[2];
-  __shared__ float s_ext[kFitWarps][2];
-  __shared__ double s_red[kFitTeamsPerCta][2 * kFitTeam * 9];  // team_sum slots: [team][parity][warp of team][9]
+  __shared__ float s_ext[T][2];
+  __shared__ double s_red[2 * T * 9];  // team_sum slots: [parity][warp][9]
   __shared__ int s_last;
+  __shared__ ScalarWs s_ws[T];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int fblock = FIT_SPLIT ? (blockIdx.x >> 1) : blockIdx.x;
-  const int hyp_cta = FIT_SPLIT ? (blockIdx.x & 1) : 0;
+  const int fblock = blockIdx.x >> 1;
+  const int hyp_cta = blockIdx.x & 1;
   const int f = w.fit_order[w.frame_base + fblock];  // big frames first (fit_order_kernel)
   ilcc2_diag* d = w.diag + f;
   float* corners = w.corners + (size_t)f * p.ncorners * 3;
@@ -2081,14 +2122,14 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 256 / kFitThrea
   if (st == ILCC2_OK && (n <= kFitBitsCap) != SMEM) return;  // the other instantiation owns this frame
   if (st != ILCC2_OK) {
     if (SMEM && hyp_cta == 0) {
-      for (int i = tid; i < p.ncorners * 3; i += kFitThreads) corners[i] = NAN;
+      for (int i = tid; i < p.ncorners * 3; i += kThreads) corners[i] = NAN;
       if (tid == 0) w.status[f] = st;
     }
     return;
   }
   const unsigned flags = w.flags ? (unsigned)w.flags[f] : w.default_flags;
   const bool autom = (flags & ILCC2_FLAG_AUTO) != 0;
-  if (FIT_SPLIT && !autom && hyp_cta == 1) return;  // manual mode: one CTA runs the requested hypotheses in sequence
+  if (!autom && hyp_cta == 1) return;  // manual mode: one CTA runs the requested hypotheses in sequence
   const float2* gyz = w.opt_yz + (size_t)f * w.cap;
   const uint8_t* gwh = w.opt_white + (size_t)f * w.cap;
   FitPts<IdxT> F;
@@ -2099,19 +2140,19 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 256 / kFitThrea
     // read through L1 (a frame's optimiser points are ~20 KB and 7 frames share an SM), which keeps the CTA's
     // shared-memory footprint at 13 KB so that registers, not shared memory, bound the residency.
     IdxT* lists = reinterpret_cast<IdxT*>(fit_sm + sizeof(uint32_t) * (kFitBitsCap / 32));
-    F.list = lists + (size_t)warp * kFitListCap;
-    F.list_cap = kFitListCap;
+    F.list = lists + (size_t)warp * (kFitTeamCap / T);
+    F.list_cap = kFitTeamCap / T;
     F.yz = gyz;
     wbits = reinterpret_cast<uint32_t*>(fit_sm);
   } else {
     uint32_t* g = w.fit_scratch + (size_t)f * w.fit_stride;
     wbits = g;
     F.yz = gyz;
-    F.list = reinterpret_cast<IdxT*>(g + (w.cap + 31) / 32 + (size_t)(hyp_cta * kFitTeam + warp) * w.cap);
+    F.list = reinterpret_cast<IdxT*>(g + (w.cap + 31) / 32 + (size_t)(hyp_cta * T + warp) * w.cap);
     F.list_cap = w.cap;
   }
   float ymax = 0.f, zmax = 0.f;
-  for (int base = warp * 32; base < n; base += kFitThreads) {  // stage points; colour flags -> one bit per point
+  for (int base = warp * 32; base < n; base += kThreads) {  // stage points; colour flags -> one bit per point
     const int k = base + lane;
     const bool v = k < n;
     const float2 q = v ? gyz[k] : make_float2(0.f, 0.f);
@@ -2148,31 +2189,34 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 256 / kFitThrea
   M.two_ha = 2.0 * p.huber_a;
   {
     float ym = 0.f, zm = 0.f;
-    for (int i = 0; i < kFitWarps; ++i) {
+    for (int i = 0; i < T; ++i) {
       ym = fmaxf(ym, s_ext[i][0]);
       zm = fmaxf(zm, s_ext[i][1]);
     }
     M.ymax_zmax = ym + zm;
   }
-  const int team_local = warp / kFitTeam, wt = warp % kFitTeam;
-  const int team = FIT_SPLIT ? hyp_cta : team_local;  // colour hypothesis this team solves in auto mode
-  if (autom || team == 0) {
+  const int wt = warp;
+  const int team = hyp_cta;  // colour hypothesis this CTA solves in auto mode
+  {
     const int h_first = autom ? team : 0;
     const int h_last = autom ? team : ((flags & ILCC2_FLAG_TOPLEFT_WHITE) ? 1 : 0);
     double x[3] = {0.0, 0.0, 0.0};
     int parity = 0;
     for (int h = h_first; h <= h_last; ++h) {  // manual mode: 'd' warm-starts hypothesis 1 from hypothesis 0
-      int evals = 0, it0 = 0, it1 = 0;
+      int evals = 0;
       double fc = 0.0;
       M.tlw = h;
-      const int term0 = solve_tr<IdxT>(&F, &M, 1, p.max_solver_iter, lane, x, &fc, &it0, &evals, s_red[team_local], &parity);  // useOutofBoard
-      if (lane == 0 && wt == 0) d->cost_a[h] = fc;
-      const int term1 = solve_tr<IdxT>(&F, &M, 0, p.max_solver_iter, lane, x, &fc, &it1, &evals, s_red[team_local], &parity);  // then without
+#pragma unroll 1
+      for (int phase = 0; phase < 2; ++phase) {  // useOutofBoard first, then without (LidarCornersEst.cpp:402-409); one call site
+        int it = 0;
+        const int term = solve_tr<IdxT, T>(&F, &M, 1 - phase, p.max_solver_iter, lane, x, &fc, &it, &evals, s_red, &parity, &s_ws[warp]);
+        if (lane == 0 && wt == 0) {
+          d->iters[h][phase] = it;
+          d->term[h][phase] = term;
+          if (phase == 0) d->cost_a[h] = fc;
+        }
+      }
       if (lane == 0 && wt == 0) {
-        d->iters[h][0] = it0;
-        d->iters[h][1] = it1;
-        d->term[h][0] = term0;
-        d->term[h][1] = term1;
         d->n_evals[h] = evals;
         d->cost[h] = fc;
         for (int i = 0; i < 3; ++i) {
@@ -2184,7 +2228,7 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 256 / kFitThrea
     }
   }
   __syncthreads();
-  if (FIT_SPLIT && autom) {
+  if (autom) {
     // the CTA of the other hypothesis publishes through diag; whichever CTA arrives second finishes the frame
     if (tid == 0) {
       __threadfence();
@@ -2216,7 +2260,7 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 256 / kFitThrea
   for (int i = 0; i < 16; ++i) pca[i] = d->pca[i];
   rigid_inverse(Topt, Ti);
   rigid_inverse(pca, Pi);
-  for (int k = tid; k < p.ncorners; k += kFitThreads) {
+  for (int k = tid; k < p.ncorners; k += kThreads) {
     const int i = 1 + k / (H - 1), j = 1 + k % (H - 1);
     const float py = (float)(((double)i - (double)W / 2.0) * p.g);
     const float pz = (float)(((double)j - (double)H / 2.0) * p.g);
@@ -2233,22 +2277,52 @@ __global__ void __launch_bounds__(kFitThreads, SMEM ? FIT_MINB : 256 / kFitThrea
   }
 }
 
-size_t fit_smem_bytes() {
-  return sizeof(uint32_t) * (kFitBitsCap / 32) + kFitWarps * sizeof(uint16_t) * kFitListCap;
+size_t fit_smem_bytes(int team) {
+  (void)team;
+  return sizeof(uint32_t) * (kFitBitsCap / 32) + sizeof(uint16_t) * kFitTeamCap;
+}
+
+// Team size for a launch of `frames` frames: the largest T in {2, 4, 8} for which all 2 * frames CTAs are resident at
+// once (128 registers per thread -> 16 warps per SM).  Large batches are throughput-bound (T = 2 keeps the redundant
+// scalar work low); small ones are bound by the latency of a single solve, which more warps per solve shorten.
+int fit_team_size(int frames, int num_sms) {
+#ifdef FIT_FORCE_TEAM
+  return FIT_FORCE_TEAM;
+#endif
+  const long long warps = (long long)FIT_WARPS_PER_SM * num_sms;
+  if (2ll * frames * 8 <= warps) return 8;
+  if (2ll * frames * 4 <= warps) return 4;
+  if (2ll * frames * 4 <= 5 * warps) return 2;  // up to 2.5 waves of two-warp teams (measured: 1024 frames 3.0 vs 3.7 ms)
+  return 1;                                     // throughput regime: no redundant scalar work (2048 frames 5.2 vs 6.0 ms)
+}
+
+template <int T>
+static void launch_fit_smem(const Workspace& w, const DevParams& p, cudaStream_t s) {
+  board_fit_kernel<true, T><<<2 * w.n_frames, 32 * T, fit_smem_bytes(T), s>>>(w, p);
 }
 
 void launch_board_fit(const Workspace& w, const DevParams& p, cudaStream_t s) {
   fit_order_kernel<<<1, 1024, 0, s>>>(w, w.num_sms);
-  const int grid = (FIT_SPLIT ? 2 : 1) * w.n_frames;
-  board_fit_kernel<true><<<grid, kFitThreads, fit_smem_bytes(), s>>>(w, p);
-  if (w.cap > kFitBitsCap) board_fit_kernel<false><<<grid, kFitThreads, 0, s>>>(w, p);
+  switch (fit_team_size(w.n_frames, w.num_sms)) {
+    case 1: launch_fit_smem<1>(w, p, s); break;
+    case 2: launch_fit_smem<2>(w, p, s); break;
+    case 4: launch_fit_smem<4>(w, p, s); break;
+    default: launch_fit_smem<8>(w, p, s); break;
+  }
+  if (w.cap > kFitBitsCap) board_fit_kernel<false, kFitGlobalTeam><<<2 * w.n_frames, 32 * kFitGlobalTeam, 0, s>>>(w, p);
 }
 
 cudaError_t configure_kernels() {
   cudaError_t e;
   e = cudaFuncSetAttribute(cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem_bytes());
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(board_fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem_bytes());
+  e = cudaFuncSetAttribute(board_fit_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem_bytes(1));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(board_fit_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem_bytes(2));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(board_fit_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem_bytes(4));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(board_fit_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem_bytes(8));
   return e;
 }
 

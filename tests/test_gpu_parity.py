@@ -215,3 +215,63 @@ def test_solver_state_agrees_with_oracle(api, oracle):
         assert np.allclose(diags[f]["cost"], diags_o[f]["cost"], rtol=1e-9, atol=1e-12)
         assert np.allclose(diags[f]["cost_a"], diags_o[f]["cost_a"], rtol=1e-9, atol=1e-12)
         assert np.abs(corners[f].astype(np.float64) - corners_o[f]).max() < 1e-6
+
+
+def test_online_variant_parameters(api, oracle, bag_clouds, fixtures):
+    """LidarCornersEst::get_chessboard_by_point (LidarCornersEst.cpp:72-115, driven by lidar_chessboard_online.cpp:70-103):
+    the same stages with cluster tolerance 0.10, the `< 500 plane points` gate and gray-zone rate 3.0
+    (lidar_chessboard_online.cpp gray_zone_rate) -- reachable through ilcc2_params.  Bag 6's plane has 1375 points with
+    the offline tolerance; the tighter tolerance changes the clusters, and a 5000-point gate must reject every frame."""
+    from lidar_camera_calibration_b200 import synth
+    for extra in (dict(), dict(min_board_points=5000)):
+        kw = dict(cluster_tolerance=0.10, min_board_points=500, gray_rate=3.0)
+        kw.update(extra)
+        p_g, p_o = api.default_params(**kw), oracle.default_params(**kw)
+        ex = api.CornerExtractor(1, 30000, params=p_g)
+        for b in (1, 2, 3, 5, 6):
+            rec = bag_clouds[b]
+            click = np.asarray(fixtures["lidar_corners"][str(b)]).mean(0).astype(np.float32)
+            st, corners, diags = ex.extract(rec[None], click[None], flags=api.FLAG_AUTO, want_diag=True)
+            st_o, c_o, d_o, roi_o, clu_o, brd_o = oracle.extract_frame(rec, click, flags=oracle.FLAG_AUTO, params=p_o,
+                                                                      want_indices=True)
+            assert st[0] == st_o and diags[0]["n_board"] == d_o["n_board"] and diags[0]["click_in_cluster"] == d_o["click_in_cluster"]
+            assert np.array_equal(ex.fetch_indices(0, 1), clu_o)
+            if "min_board_points" in extra:
+                assert st[0] == 3  # ILCC2_PLANE_TOO_SMALL
+            elif st_o == 0:
+                assert np.array_equal(diags[0]["gray"], d_o["gray"])
+                assert np.linalg.norm(corners[0].astype(np.float64) - c_o, axis=1).max() <= TOL_CORNER_M
+    F = 12
+    pts, clicks = synth.make_batch(F, start=300)
+    kw = dict(cluster_tolerance=0.10, min_board_points=500, gray_rate=3.0)
+    ex = api.CornerExtractor(F, synth.VLP16.n_points, params=api.default_params(**kw))
+    st, corners = ex.extract(pts, clicks, flags=api.FLAG_AUTO)
+    st_o, corners_o = oracle.extract_batch(pts, clicks, flags=oracle.FLAG_AUTO, params=oracle.default_params(**kw), threads=4)
+    assert np.array_equal(st, st_o)
+    ok = st == 0
+    assert np.abs(corners[ok].astype(np.float64) - corners_o[ok]).max() <= TOL_CORNER_M
+
+
+def test_team_sizes_agree(api, oracle):
+    """K5 puts 8 / 4 / 2 warps on a solve depending on how many frames a launch holds (launch_board_fit).  The partial
+    sums are grouped per warp, so results may differ in the last bits between team sizes -- not in iteration counts."""
+    from lidar_camera_calibration_b200 import synth
+    F = 320                                     # one launch of 320 frames -> teams of 2
+    pts, clicks = synth.make_batch(F, start=4000)
+    ex = api.CornerExtractor(F, synth.VLP16.n_points)
+    st2, c2, d2 = ex.extract(pts, clicks, flags=api.FLAG_AUTO, want_diag=True)
+    st4, c4, d4 = ex.extract(pts[:200], clicks[:200], flags=api.FLAG_AUTO, want_diag=True)   # 200 frames -> teams of 4
+    st8, c8, d8 = ex.extract(pts[:64], clicks[:64], flags=api.FLAG_AUTO, want_diag=True)     # 64 frames -> teams of 8
+    for st, c, d, n in ((st4, c4, d4, 200), (st8, c8, d8, 64)):
+        assert np.array_equal(st, st2[:n])
+        ok = st == 0
+        assert np.abs(c[ok] - c2[:n][ok]).max() < 1e-6
+        for f in range(n):
+            if ok[f]:
+                assert np.array_equal(d[f]["iters"], d2[f]["iters"]) and np.array_equal(d[f]["term"], d2[f]["term"])
+                assert np.allclose(d[f]["theta_t"], d2[f]["theta_t"], rtol=0, atol=1e-9)
+    st_o, c_o = oracle.extract_batch(pts[:64], clicks[:64], flags=oracle.FLAG_AUTO, threads=4)
+    assert np.array_equal(st_o, st2[:64])
+    ok = st_o == 0
+    for c in (c2[:64], c4[:64], c8):
+        assert np.abs(c[ok].astype(np.float64) - c_o[ok]).max() <= TOL_CORNER_M
