@@ -44,23 +44,17 @@ def hbm_peak():
 
 
 def ncu_traffic():
-    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel from the committed
-    `ncu --set full` summaries under profiles/ (same workload: 1024 frames). Returns {stage: bytes}."""
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel, from the newest committed
+    `ncu --set full` capture of this workload (1024 frames): profiles/ncu_traffic_*.json, written by
+    tools/ncu_summary.py next to the text summaries. Returns {stage: bytes}."""
     import glob
-    import re
-    out = {}
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_*_r1c.txt"))):
-        name = None
-        for line in open(path):
-            m = re.match(r"== (?:void )?(\w+?)(?:_kernel)?(?:<(\d)>)?\(", line)
-            if m:
-                name = m.group(1) if m.group(2) in (None, "1") or m.group(1) == "roi_filter" else None
-                continue
-            m = re.search(r"dram__bytes_(read|write)\.sum = ([0-9.]+) (\w+)", line)
-            if m and name:
-                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m.group(3)]
-                out[name] = out.get(name, 0.0) + float(m.group(2)) * mult
-    return out
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_traffic_*.json")))
+    if not paths:
+        return {}
+    try:
+        return {k: v["dram_bytes"] for k, v in json.load(open(paths[-1])).items()}
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -206,7 +200,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
@@ -312,6 +306,28 @@ def main():
     pnp = pnp_leg(api, ldist, synth, torch, dev, rank, world, rank * F, gt,
                   g_corners if world > 1 else d_corners, g_status if world > 1 else d_status)
 
+    # ---- projecting the batch's points through the extrinsic (spaceToPlane + colouring) ----
+    proj = None
+    if rank == 0:
+        pj = api.PnpSolver(local)
+        flat = d_pts.view(-1, 4)
+        pix = torch.empty((flat.shape[0], 2), dtype=torch.int32, device=dev)
+        rgbv = torch.empty((flat.shape[0], 4), dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            pj.project_points(flat, synth.PLANTED_EXTRINSIC, synth.PLANTED_CAMERA, 1920, 1200, pix=pix, rgbv=rgbv)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for _ in range(10):
+            pj.project_points(flat, synth.PLANTED_EXTRINSIC, synth.PLANTED_CAMERA, 1920, 1200, pix=pix, rgbv=rgbv)
+        p1.record(stream)
+        torch.cuda.synchronize(dev)
+        pms = p0.elapsed_time(p1) / 10
+        pbytes = flat.shape[0] * (16 + 8 + 4)
+        proj = {"points": int(flat.shape[0]), "ms": pms, "points_per_s": flat.shape[0] / (pms * 1e-3),
+                "algorithmic_bytes": pbytes, "achieved_gbs": pbytes / (pms * 1e-3) / 1e9,
+                "valid_points": int(rgbv[:, 3].sum().item()),
+                "note": "ilcc2_project_points over the step's 1024 x 28800 points: 16 B in, 12 B out per point"}
+
     if rank != 0:
         torch.distributed.destroy_process_group()
         return
@@ -352,6 +368,7 @@ def main():
                             note="the only kernel that reads all input bytes"),
         "kernel_ms_per_step": per_launch_ms,
         "pnp": pnp,
+        "projection": dict(proj, frac_of_hbm_peak=proj["achieved_gbs"] / peak) if proj else None,
         "workload_gen_s": gen_s,
     }
     if not args.no_cpu_baseline and world == 1:

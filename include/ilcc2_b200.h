@@ -218,6 +218,20 @@ int ilcc2_pnp_solve(ilcc2_pnp* h, const double* pts3, const double* pts2, const 
                     const double camera[4], double huber_delta, int max_iterations, double r[3], double t[3],
                     ilcc2_pnp_summary* summary, int mem_kind, void* stream);
 
+/* Using the calibration: ImageCornersEst::spaceToPlane (ImageCornersEst.cpp:135-155) for every
+ * point of a cloud plus the colouring loops of ilcc2/test/pcd2image.cpp:59-84 and ilcc2/test/rgblidar.cpp:53-73.
+ *   P_c = R * P_w + t with [R|t] = T_lidar2cam (row-major 4x4, what txt2extrinsic reads back from <pose_file>);
+ *   a point is valid iff 0 <= P_c.z <= distance_valid and 0 < u < width, 0 < v < height (u = fx x/z + cx, ...).
+ *   pix_xy_out  [n][2] int32: (int)u, (int)v -- or (-1, -1) for an invalid point
+ *   rgbv_out    [n][4] uint8: r, g, b, valid.  image_bgr == NULL: HSVtoRGB((I - inten_low) / (inten_high - inten_low)
+ *               * 255, 100, 100) as pcd2image does (it uses inten_low 0, inten_high 60, distance_valid 5);
+ *               else the bgr8 pixel [v][u] of image_bgr ([height][width][3]) as rgblidar does.
+ * Point records as in ilcc2_extract_corners.  camera = fx, cx, fy, cy and T_lidar2cam are HOST pointers. */
+int ilcc2_project_points(ilcc2_pnp* h, const void* points, int64_t n_points, int point_step, int off_x, int off_y,
+                         int off_z, int off_intensity, const double T_lidar2cam[16], const double camera[4], int width,
+                         int height, double distance_valid, double inten_low, double inten_high,
+                         const uint8_t* image_bgr, int32_t* pix_xy_out, uint8_t* rgbv_out, int mem_kind, void* stream);
+
 /* T_lidar2cam = [AngleAxis(|r|, r/|r|) | t] * T_axis_roughly (Optimization.cpp:75-88, calib_lidar_cam.cpp:157-160). */
 int ilcc2_compose_extrinsic(const double r[3], const double t[3], const double T_axis[16], double T_out_rowmajor[16]);
 

@@ -18,7 +18,7 @@ EXPORTS = [
     "ilcc2_set_profiling", "ilcc2_stage_times", "ilcc2_launch_count", "ilcc2_save_corners2txt", "ilcc2_shard_range",
     "ilcc2_pnp_create", "ilcc2_pnp_destroy", "ilcc2_pnp_last_error", "ilcc2_pnp_launch_count", "ilcc2_axis_roughly",
     "ilcc2_pnp_order_corners", "ilcc2_pnp_solve", "ilcc2_compose_extrinsic", "ilcc2_extrinsic2bin",
-    "ilcc2_read_cam_corners", "ilcc2_read_lidar_corners", "ilcc2_read_camera_yaml",
+    "ilcc2_read_cam_corners", "ilcc2_read_lidar_corners", "ilcc2_read_camera_yaml", "ilcc2_project_points",
 ]
 
 
@@ -112,6 +112,10 @@ def load() -> C.CDLL:
     L.ilcc2_pnp_solve.restype = C.c_int
     L.ilcc2_pnp_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double,
                                   C.c_int, C.c_void_p, C.c_void_p, C.POINTER(PnpSummary), C.c_int, C.c_void_p]
+    L.ilcc2_project_points.restype = C.c_int
+    L.ilcc2_project_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.ilcc2_compose_extrinsic.restype = C.c_int
     L.ilcc2_compose_extrinsic.argtypes = [C.c_void_p] * 4
     L.ilcc2_extrinsic2bin.restype = C.c_int

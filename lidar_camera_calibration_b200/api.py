@@ -440,3 +440,37 @@ class PnpSolver:
                                                 camera.ctypes.data, huber, max_iterations, r.ctypes.data,
                                                 t.ctypes.data, C.byref(sm), MEM_HOST, None))
         return r, t, {k: getattr(sm, k) for k, _ in _lib.PnpSummary._fields_}
+
+    def project_points(self, points, T_lidar2cam, camera, width: int, height: int, distance_valid: float = 5.0,
+                       inten_low: float = 0.0, inten_high: float = 60.0, image_bgr=None, pix=None, rgbv=None):
+        """ImageCornersEst::spaceToPlane for every point + the colouring of pcd2image.cpp:59-84 (image_bgr None: HSV of
+        the intensity) or rgblidar.cpp:53-73 (colour of the pixel).  points (n, 4|8) float32, numpy or torch CUDA.
+        Returns (pix (n,2) int32, rgbv (n,4) uint8 = r, g, b, valid)."""
+        T = np.ascontiguousarray(T_lidar2cam, np.float64)
+        cam = np.ascontiguousarray(camera, np.float64)
+        if _is_torch(points):
+            import torch
+            assert points.is_cuda and points.dtype == torch.float32 and points.is_contiguous() and points.dim() == 2
+            n, wdt = points.shape
+            step, ox, oy, oz, oi = _layout(wdt)
+            if pix is None:
+                pix = torch.empty((n, 2), dtype=torch.int32, device=points.device)
+            if rgbv is None:
+                rgbv = torch.empty((n, 4), dtype=torch.uint8, device=points.device)
+            img = image_bgr.contiguous() if image_bgr is not None else None
+            stream = torch.cuda.current_stream(points.device).cuda_stream
+            self._check(self._L.ilcc2_project_points(
+                self._h, points.data_ptr(), n, step, ox, oy, oz, oi, T.ctypes.data, cam.ctypes.data, width, height,
+                distance_valid, inten_low, inten_high, img.data_ptr() if img is not None else None, pix.data_ptr(),
+                rgbv.data_ptr(), MEM_DEVICE, stream))
+            return pix, rgbv
+        pts = np.ascontiguousarray(points, np.float32)
+        n, wdt = pts.shape
+        step, ox, oy, oz, oi = _layout(wdt)
+        pix, rgbv = np.empty((n, 2), np.int32), np.empty((n, 4), np.uint8)
+        img = np.ascontiguousarray(image_bgr, np.uint8) if image_bgr is not None else None
+        self._check(self._L.ilcc2_project_points(
+            self._h, pts.ctypes.data, n, step, ox, oy, oz, oi, T.ctypes.data, cam.ctypes.data, width, height,
+            distance_valid, inten_low, inten_high, img.ctypes.data if img is not None else None, pix.ctypes.data,
+            rgbv.ctypes.data, MEM_HOST, None))
+        return pix, rgbv

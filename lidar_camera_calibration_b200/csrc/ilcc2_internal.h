@@ -28,7 +28,7 @@ struct DevParams {
   int ncorners;
 };
 
-constexpr int kRoiThreads = 512;      // K1 CTA size
+constexpr int kRoiThreads = 512;      // K1 CTA size for small batches (128 for batches of >= 4 frames per SM)
 constexpr int kRoiUnroll = 4;         // K1 records per thread per tile
 constexpr int kClusterThreads = 256;  // K2 CTA size
 constexpr int kClusterSmemPts = 4096; // K2: frames with at most this many ROI points cluster in shared memory

@@ -123,12 +123,13 @@ __device__ __forceinline__ float4 load_point(const unsigned char* rec, int ox, i
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kRoiThreads) roi_filter_kernel(const Workspace w, const DevParams p) {
-  constexpr int NT = kRoiThreads, U = kRoiUnroll, TILE = NT * U, NW = NT / 32;
-  __shared__ int s_cnt[U * NW];
-  __shared__ int s_off[U * NW];
-  __shared__ int s_tile_total;
+// NT threads per CTA, 1024 threads (64 registers each) resident per SM.  Large batches use small CTAs (NT = 128: all
+// 1024 frames of the bench batch are resident in ONE wave, 0.091 ms = 5.2 TB/s; NT = 512 has 3.5 waves and a 13 %
+// tail, 0.098 ms), small batches use large ones (a single frame is streamed by whatever one CTA has in flight).
+template <int MODE, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) roi_filter_kernel(const Workspace w, const DevParams p) {
+  constexpr int U = kRoiUnroll, TILE = NT * U, NW = NT / 32;
+  __shared__ int s_cnt[2][U * NW];
   __shared__ unsigned long long s_key[NW];
 
   const int f = blockIdx.x + w.frame_base, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(kRoiThreads) roi_filter_kernel(const Workspace
     }
     bool pr[U];
     int rank[U];
+    int* cnt = s_cnt[(tile0 / TILE) & 1];  // double-buffered: one barrier per tile is enough
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const float4 v = cur[u];
@@ -180,13 +182,14 @@ __global__ void __launch_bounds__(kRoiThreads) roi_filter_kernel(const Workspace
       pr[u] = ok;
       const unsigned b = __ballot_sync(FULL, ok);
       rank[u] = __popc(b & ((1u << lane) - 1u));
-      if (lane == 0) s_cnt[u * NW + warp] = __popc(b);
+      if (lane == 0) cnt[u * NW + warp] = __popc(b);
     }
     __syncthreads();
-    if (warp == 0) {
-      // exclusive scan of the U*NW (= 64) counts, u-major = input order
-      static_assert(U * NW == 64, "scan below assumes 64 counts");
-      const int a = s_cnt[lane], b = s_cnt[32 + lane];
+    // every warp scans the U*NW (= 64) counts itself (u-major = input order): no serial section, no second barrier
+    static_assert(U * NW <= 64, "scan below handles at most 64 counts");
+    int my_off[U], tile_total;
+    {
+      const int a = lane < U * NW ? cnt[lane] : 0, b = 32 + lane < U * NW ? cnt[32 + lane] : 0;
       int sa = a, sb = b;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -197,15 +200,19 @@ __global__ void __launch_bounds__(kRoiThreads) roi_filter_kernel(const Workspace
         }
       }
       const int tot_a = __shfl_sync(FULL, sa, 31);
-      s_off[lane] = sa - a;
-      s_off[32 + lane] = tot_a + sb - b;
-      if (lane == 31) s_tile_total = tot_a + sb;
+      tile_total = tot_a + __shfl_sync(FULL, sb, 31);
+      const int ex_a = sa - a, ex_b = tot_a + sb - b;  // exclusive offsets of counts lane and 32 + lane
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = u * NW + warp;  // this warp's count for sub-tile u
+        const int va = __shfl_sync(FULL, ex_a, idx & 31), vb = __shfl_sync(FULL, ex_b, idx & 31);
+        my_off[u] = idx < 32 ? va : vb;
+      }
     }
-    __syncthreads();
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (pr[u]) {
-        const int k = total + s_off[u * NW + warp] + rank[u];
+        const int k = total + my_off[u] + rank[u];
         const float4 v = cur[u];
         if (k < w.cap) {
           out_pts[k] = v;
@@ -216,7 +223,7 @@ __global__ void __launch_bounds__(kRoiThreads) roi_filter_kernel(const Workspace
         best = key < best ? key : best;
       }
     }
-    total += s_tile_total;
+    total += tile_total;
 #pragma unroll
     for (int u = 0; u < U; ++u) cur[u] = nxt[u];
   }
@@ -240,13 +247,21 @@ __global__ void __launch_bounds__(kRoiThreads) roi_filter_kernel(const Workspace
   }
 }
 
-void launch_roi_filter(const Workspace& w, const DevParams& p, cudaStream_t s) {
+template <int NT>
+static void launch_roi_filter_nt(const Workspace& w, const DevParams& p, cudaStream_t s) {
   if (w.step == 16 && w.ox == 0 && w.oy == 4 && w.oz == 8 && w.oi == 12)
-    roi_filter_kernel<0><<<w.n_frames, kRoiThreads, 0, s>>>(w, p);
+    roi_filter_kernel<0, NT><<<w.n_frames, NT, 0, s>>>(w, p);
   else if (w.step == 32 && w.ox == 0 && w.oy == 4 && w.oz == 8 && w.oi == 16)
-    roi_filter_kernel<1><<<w.n_frames, kRoiThreads, 0, s>>>(w, p);
+    roi_filter_kernel<1, NT><<<w.n_frames, NT, 0, s>>>(w, p);
   else
-    roi_filter_kernel<2><<<w.n_frames, kRoiThreads, 0, s>>>(w, p);
+    roi_filter_kernel<2, NT><<<w.n_frames, NT, 0, s>>>(w, p);
+}
+
+void launch_roi_filter(const Workspace& w, const DevParams& p, cudaStream_t s) {
+  if (w.n_frames >= 4 * w.num_sms)
+    launch_roi_filter_nt<128>(w, p, s);
+  else
+    launch_roi_filter_nt<kRoiThreads>(w, p, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1540,6 +1555,9 @@ struct Dogleg {
   int sub1d;
   double U[3][2], sub_g[2], sub_B[3];
   double step_norm;
+  // values that only change when the Gauss-Newton step / subspace model is rebuilt, cached for the (many) rejected
+  // iterations that reuse it: |gn|, and eigenvalues of sub_B and |sub_g| for the boundary problem
+  double gnn, tb_l1, tb_l2, tb_gn;
 };
 
 // Per-warp scratch of the scalar solver, kept in SHARED memory: the out-of-line dogleg routines take these by
@@ -1614,26 +1632,25 @@ __device__ bool tr2_eval(double a, double b, double dd, double g0, double g1, do
 }
 
 // min 1/2 x'Bx + g'x on |x| = radius: safeguarded Newton on 1/|x(y)| - 1/radius, x(y) = -(B + yI)^-1 g
-__device__ __noinline__ bool tr_boundary_2d(const double B[3], const double g[2], double radius, double x_out[2]) {
+__device__ __noinline__ bool tr_boundary_2d(const double B[3], const double g[2], double l1, double l2, double gn,
+                                            double radius, double x_out[2]) {
   const double a = B[0], b = B[1], dd = B[2];
-  const double tr = a + dd, hd = 0.5 * (a - dd);
-  const double disc = dsqrt(hd * hd + b * b);
-  const double l1 = 0.5 * tr - disc, l2 = 0.5 * tr + disc;
-  const double gn = dsqrt(g[0] * g[0] + g[1] * g[1]);
   x_out[0] = 0.0;
   x_out[1] = 0.0;
   if (!(gn > 0.0) || !(radius > 0.0)) return false;
-  double lo = ddiv(gn, radius) - l2;
+  const double gr = ddiv(gn, radius);
+  double lo = gr - l2;
   if (lo < -l1) lo = -l1;
-  double hi = ddiv(gn, radius) - l1;
+  double hi = gr - l1;
   if (!(hi > lo)) hi = lo + fabs(lo) * 1e-12 + 1e-300;
   double y = 0.0;
   if (y < lo || y > hi) y = lo;
   double x[2] = {0.0, 0.0}, n2 = 0.0, q = 0.0;
   bool have = false;
 #ifndef NO_FAST_TR2
-  const double inv_radius = ddiv(1.0, radius);
+  const double inv_radius = (radius > 1e-280 && radius < 1e280) ? fast_rcp(radius) : ddiv(1.0, radius);  // Newton update only
 #endif
+  double n_last = 0.0;
   for (int it = 0; it < 100; ++it) {
     if (!tr2_eval(a, b, dd, g[0], g[1], y, x, n2, q)) {
       lo = y;
@@ -1645,11 +1662,13 @@ __device__ __noinline__ bool tr_boundary_2d(const double B[3], const double g[2]
 #ifndef NO_FAST_TR2
     const bool fast_ok = n2 > 1e-280 && n2 < 1e280 && fabs(q) > 1e-280 && fabs(q) < 1e280;
     const double n = fast_ok ? fast_sqrt_pos(n2) : dsqrt(n2);
+    n_last = n;
     if (fabs(n - radius) <= 1e-14 * radius) break;
     if (n > radius) lo = y; else hi = y;
     double yn = fast_ok ? y + ((n - radius) * inv_radius) * (n2 * fast_rcp(q)) : y + ddiv(n - radius, radius) * ddiv(n2, q);
 #else
     const double n = dsqrt(n2);
+    n_last = n;
     if (fabs(n - radius) <= 1e-14 * radius) break;
     if (n > radius) lo = y; else hi = y;
     double yn = y + ddiv(n - radius, radius) * ddiv(n2, q);
@@ -1659,15 +1678,14 @@ __device__ __noinline__ bool tr_boundary_2d(const double B[3], const double g[2]
     y = yn;
   }
   if (!have) return false;
-  const double n = dsqrt(n2);
-  if (!(fabs(n - radius) <= 1e-6 * radius)) return false;
+  if (!(fabs(n_last - radius) <= 1e-6 * radius)) return false;  // n_last = |x| of the last evaluated multiplier
   x_out[0] = x[0];
   x_out[1] = x[1];
   return true;
 }
 
 __device__ void dogleg_traditional(Dogleg& S, double step[3]) {
-  const double gnorm = norm3(S.grad), gnn = norm3(S.gn);
+  const double gnorm = norm3(S.grad), gnn = S.gnn;
   if (gnn <= S.radius) {
     for (int i = 0; i < 3; ++i) step[i] = ddiv(S.gn[i], S.diag[i]);
     S.step_norm = gnn;
@@ -1691,7 +1709,7 @@ __device__ void dogleg_traditional(Dogleg& S, double step[3]) {
 }
 
 __device__ void dogleg_subspace_step(Dogleg& S, double step[3]) {
-  const double gnn = norm3(S.gn);
+  const double gnn = S.gnn;
   if (gnn <= S.radius) {
     for (int i = 0; i < 3; ++i) step[i] = ddiv(S.gn[i], S.diag[i]);
     S.step_norm = gnn;
@@ -1704,7 +1722,7 @@ __device__ void dogleg_subspace_step(Dogleg& S, double step[3]) {
     return;
   }
   double m2[2];
-  if (!tr_boundary_2d(S.sub_B, S.sub_g, S.radius, m2)) {
+  if (!tr_boundary_2d(S.sub_B, S.sub_g, S.tb_l1, S.tb_l2, S.tb_gn, S.radius, m2)) {
     dogleg_traditional(S, step);
     return;
   }
@@ -1748,6 +1766,7 @@ __device__ __noinline__ bool dogleg_compute_step(Dogleg& S, const double Hs[6], 
   if (!ok) return false;
   for (int i = 0; i < 3; ++i) S.gn[i] = -S.diag[i] * y[i];
   const double n_g = norm3(S.grad), n_n = norm3(S.gn);
+  S.gnn = n_n;
   const bool gfirst = n_g >= n_n;
   const double na = gfirst ? n_g : n_n;
   if (!(na > 0.0)) return false;
@@ -1777,6 +1796,11 @@ __device__ __noinline__ bool dogleg_compute_step(Dogleg& S, const double Hs[6], 
     S.sub_B[0] = quad3(Hs, w0, w0);
     S.sub_B[1] = quad3(Hs, w0, w1);
     S.sub_B[2] = quad3(Hs, w1, w1);
+    const double tr = S.sub_B[0] + S.sub_B[2], hd = 0.5 * (S.sub_B[0] - S.sub_B[2]);
+    const double disc = dsqrt(hd * hd + S.sub_B[1] * S.sub_B[1]);
+    S.tb_l1 = 0.5 * tr - disc;
+    S.tb_l2 = 0.5 * tr + disc;
+    S.tb_gn = dsqrt(S.sub_g[0] * S.sub_g[0] + S.sub_g[1] * S.sub_g[1]);
   }
   dogleg_subspace_step(S, step);
   return true;
@@ -1872,6 +1896,8 @@ __device__ FIT_SOLVE_ATTR int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp
   S.sub1d = 0;
   S.alpha = 0.0;
   S.step_norm = 0.0;
+  S.gnn = 0.0;
+  S.tb_l1 = S.tb_l2 = S.tb_gn = 0.0;
   int iter = 0, invalid = 0, term = TERM_MAX_ITER, n_evals = 0;
   bool succ = true, first = true;
 #ifdef FIT_TIMING
@@ -1970,7 +1996,7 @@ __device__ FIT_SOLVE_ATTR int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp
       }
     } else {
       succ = false;
-      const double gnn = norm3(S.gn);
+      const double gnn = S.gnn;
       const bool was_gn = gnn <= S.radius;
       S.radius *= 0.5;
       S.reuse = 1;

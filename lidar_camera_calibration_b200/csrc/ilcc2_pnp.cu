@@ -539,6 +539,78 @@ __global__ void order_corners_kernel(const float* __restrict__ lidar, const int3
   if (valid_out) valid_out[gid] = (!status || status[f] == ILCC2_OK) ? 1 : 0;
 }
 
+// ImageCornersEst::spaceToPlane (ImageCornersEst.cpp:135-155) + the per-point colouring of pcd2image.cpp:59-84
+// (HSVtoRGB of the intensity, ImageCornersEst.cpp:372-428) or rgblidar.cpp:53-73 (colour of the pixel the point falls on).
+// One thread per point, grid-stride; 16 or 32 B in, 12 B out per point: HBM-bound.
+struct ProjParams {
+  double R[9], t[3], fx, cx, fy, cy, dist, inten_low, inten_high;
+  int width, height, step, ox, oy, oz, oi;
+};
+
+__device__ __forceinline__ uchar4 hsv_to_rgb_100(int h) {  // HSVtoRGB(h, 100, 100, ...): S = V = 100
+  const float RGB_max = 100 * 2.55f;
+  const float RGB_min = RGB_max * (100 - 100) / 100.0f;
+  const int i = h / 60, difs = h % 60;
+  const float adj = (RGB_max - RGB_min) * difs / 60.0f;
+  float r, g, b;
+  switch (i) {
+    case 0: r = RGB_max; g = RGB_min + adj; b = RGB_min; break;
+    case 1: r = RGB_max - adj; g = RGB_max; b = RGB_min; break;
+    case 2: r = RGB_min; g = RGB_max; b = RGB_min + adj; break;
+    case 3: r = RGB_min; g = RGB_max - adj; b = RGB_max; break;
+    case 4: r = RGB_min + adj; g = RGB_min; b = RGB_max; break;
+    default: r = RGB_max; g = RGB_min; b = RGB_max - adj; break;
+  }
+  // float -> unsigned char as the reference's implicit conversion (truncation); values outside 0..255 are undefined
+  // behaviour there (negative hue) and are clamped here
+  auto cv8 = [](float v) { return (unsigned char)(int)fminf(fmaxf(v, 0.f), 255.f); };
+  return make_uchar4(cv8(r), cv8(g), cv8(b), 1);
+}
+
+template <int MODE>  // 0: packed 16-byte XYZI, 1: 32-byte records (x,y,z@0, intensity@16), 2: generic offsets
+__global__ void __launch_bounds__(256) project_points_kernel(const unsigned char* __restrict__ pts, long long n,
+                                                             const ProjParams P, const unsigned char* __restrict__ image,
+                                                             int2* __restrict__ pix, uchar4* __restrict__ rgb) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float x, y, z, in;
+    const unsigned char* rec = pts + (size_t)i * P.step;
+    if (MODE == 0) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(rec));
+      x = v.x; y = v.y; z = v.z; in = v.w;
+    } else if (MODE == 1) {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(rec));
+      x = a.x; y = a.y; z = a.z;
+      in = __ldcs(reinterpret_cast<const float*>(rec + 16));
+    } else {
+      x = *reinterpret_cast<const float*>(rec + P.ox);
+      y = *reinterpret_cast<const float*>(rec + P.oy);
+      z = *reinterpret_cast<const float*>(rec + P.oz);
+      in = *reinterpret_cast<const float*>(rec + P.oi);
+    }
+    const double X = (double)x, Y = (double)y, Z = (double)z;
+    const double pcx = ((P.R[0] * X + P.R[1] * Y) + P.R[2] * Z) + P.t[0];  // Eigen: m_R * P_w + m_t
+    const double pcy = ((P.R[3] * X + P.R[4] * Y) + P.R[5] * Z) + P.t[1];
+    const double pcz = ((P.R[6] * X + P.R[7] * Y) + P.R[8] * Z) + P.t[2];
+    int2 px = make_int2(-1, -1);
+    uchar4 c = make_uchar4(0, 0, 0, 0);
+    if (!(pcz < 0.0 || pcz > P.dist)) {
+      const double u = P.fx * (pcx / pcz) + P.cx, v = P.fy * (pcy / pcz) + P.cy;
+      if (u > 0.0 && u < (double)P.width && v > 0.0 && v < (double)P.height) {
+        px = make_int2((int)u, (int)v);
+        if (image) {
+          const unsigned char* q = image + ((size_t)px.y * P.width + px.x) * 3;  // bgr8
+          c = make_uchar4(q[2], q[1], q[0], 1);
+        } else {
+          const double h = ((double)in - P.inten_low) / (P.inten_high - P.inten_low) * 255.0;
+          c = hsv_to_rgb_100(h == h ? (int)h : 0);
+        }
+      }
+    }
+    __stcs(pix + i, px);
+    __stcs(rgb + i, c);
+  }
+}
+
 thread_local std::string g_pnp_create_error;
 
 }  // namespace
@@ -780,6 +852,65 @@ int ilcc2_pnp_solve(ilcc2_pnp* h, const double* pts3, const double* pts2, const 
     summary->termination = fin.term;
     summary->n_evals = fin.n_evals;
     summary->n_pairs = -1;  // not counted on the device
+  }
+  return ILCC2_SUCCESS;
+}
+
+int ilcc2_project_points(ilcc2_pnp* h, const void* points, int64_t n_points, int point_step, int off_x, int off_y,
+                         int off_z, int off_intensity, const double T_lidar2cam[16], const double camera[4], int width,
+                         int height, double distance_valid, double inten_low, double inten_high,
+                         const uint8_t* image_bgr, int32_t* pix_xy_out, uint8_t* rgbv_out, int mem_kind, void* stream) {
+  if (!h) return ILCC2_ERR_INVALID_ARGUMENT;
+  if (!points || !T_lidar2cam || !camera || !pix_xy_out || !rgbv_out || n_points < 1 || point_step < 16 || width < 1 ||
+      height < 1 || off_x < 0 || off_y < 0 || off_z < 0 || off_intensity < 0 || off_x + 4 > point_step ||
+      off_y + 4 > point_step || off_z + 4 > point_step || off_intensity + 4 > point_step || (point_step & 3))
+    return pfail(h, ILCC2_ERR_INVALID_ARGUMENT, "project_points: null or out-of-range argument");
+  if (mem_kind != ILCC2_MEM_HOST && mem_kind != ILCC2_MEM_DEVICE)
+    return pfail(h, ILCC2_ERR_INVALID_ARGUMENT, "mem_kind must be ILCC2_MEM_HOST or ILCC2_MEM_DEVICE");
+  PNP_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ProjParams P;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) P.R[3 * i + j] = T_lidar2cam[4 * i + j];
+    P.t[i] = T_lidar2cam[4 * i + 3];
+  }
+  P.fx = camera[0]; P.cx = camera[1]; P.fy = camera[2]; P.cy = camera[3];
+  P.dist = distance_valid; P.inten_low = inten_low; P.inten_high = inten_high;
+  P.width = width; P.height = height; P.step = point_step;
+  P.ox = off_x; P.oy = off_y; P.oz = off_z; P.oi = off_intensity;
+  const unsigned char* d_pts = static_cast<const unsigned char*>(points);
+  const unsigned char* d_img = image_bgr;
+  int2* d_pix = reinterpret_cast<int2*>(pix_xy_out);
+  uchar4* d_rgb = reinterpret_cast<uchar4*>(rgbv_out);
+  DevBuf bp, bi, bo, bc;
+  if (mem_kind == ILCC2_MEM_HOST) {
+    PNP_TRY(h, bp.upload(points, (size_t)n_points * point_step, s));
+    if (image_bgr) PNP_TRY(h, bi.upload(image_bgr, (size_t)width * height * 3, s));
+    PNP_TRY(h, bo.upload(nullptr, (size_t)n_points * sizeof(int2), s));
+    PNP_TRY(h, bc.upload(nullptr, (size_t)n_points * sizeof(uchar4), s));
+    d_pts = (const unsigned char*)bp.p;
+    d_img = image_bgr ? (const unsigned char*)bi.p : nullptr;
+    d_pix = (int2*)bo.p;
+    d_rgb = (uchar4*)bc.p;
+  }
+  const int threads = 256;
+  long long blocks = (n_points + threads - 1) / threads;
+  const long long cap = 8ll * h->num_sms * 4;  // 8 resident CTAs per SM, 4 points per thread at full size
+  if (blocks > cap) blocks = cap;
+  const bool packed = point_step == 16 && off_x == 0 && off_y == 4 && off_z == 8 && off_intensity == 12;
+  const bool pcl32 = point_step == 32 && off_x == 0 && off_y == 4 && off_z == 8 && off_intensity == 16;
+  if (packed)
+    project_points_kernel<0><<<(int)blocks, threads, 0, s>>>(d_pts, n_points, P, d_img, d_pix, d_rgb);
+  else if (pcl32)
+    project_points_kernel<1><<<(int)blocks, threads, 0, s>>>(d_pts, n_points, P, d_img, d_pix, d_rgb);
+  else
+    project_points_kernel<2><<<(int)blocks, threads, 0, s>>>(d_pts, n_points, P, d_img, d_pix, d_rgb);
+  h->launches++;
+  PNP_TRY(h, cudaGetLastError());
+  if (mem_kind == ILCC2_MEM_HOST) {
+    PNP_TRY(h, cudaMemcpyAsync(pix_xy_out, d_pix, (size_t)n_points * sizeof(int2), cudaMemcpyDeviceToHost, s));
+    PNP_TRY(h, cudaMemcpyAsync(rgbv_out, d_rgb, (size_t)n_points * sizeof(uchar4), cudaMemcpyDeviceToHost, s));
+    PNP_TRY(h, cudaStreamSynchronize(s));
   }
   return ILCC2_SUCCESS;
 }

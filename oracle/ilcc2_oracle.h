@@ -153,6 +153,10 @@ void ilcc2o_pnp_residual(const double p3[3], const double p2[2], const double ca
 int ilcc2o_solve_pnp(const double* p3, const double* p2, const uint8_t* valid /*nullable*/, int32_t m,
                      const double cam[4], double huber, int32_t max_iter, double r[3], double t[3],
                      ilcc2o_pnp_summary* out);
+void ilcc2o_project_points(const void* points, int64_t n, int32_t step, int32_t ox, int32_t oy, int32_t oz, int32_t oi,
+                           const double T_lidar2cam[16], const double cam[4], int32_t width, int32_t height,
+                           double distance_valid, double inten_low, double inten_high, const uint8_t* image_bgr /*nullable*/,
+                           int32_t* pix_xy, uint8_t* rgbv);
 void ilcc2o_compose_extrinsic(const double r[3], const double t[3], const double T_axis[16], double T_out[16]);
 
 /* test-only: record the evaluation points of the solves run by the calling thread (4 doubles each: x[0..2], kind) */

@@ -555,3 +555,72 @@ void ilcc2o_compose_extrinsic(const double r[3], const double t[3], const double
       T_out[4 * i + j] = s;
     }
 }
+
+/* ---------------------------------------------------------------------------------------------- */
+/* ImageCornersEst::spaceToPlane (ImageCornersEst.cpp:135-155), HSVtoRGB (:372-428) and the per-point  */
+/* loops of test/pcd2image.cpp:59-84 (image == NULL) / test/rgblidar.cpp:53-73 (image = bgr8).         */
+/* pix [n][2] int32 ((-1,-1) = not valid), rgbv [n][4] = r, g, b, valid.                              */
+/* ---------------------------------------------------------------------------------------------- */
+static void hsv_to_rgb(int h, int s, int v, unsigned char* r, unsigned char* g, unsigned char* b) {
+  float RGB_min, RGB_max;
+  RGB_max = v * 2.55f;
+  RGB_min = RGB_max * (100 - s) / 100.0f;
+  const int i = h / 60;
+  const int difs = h % 60;
+  const float RGB_Adj = (RGB_max - RGB_min) * difs / 60.0f;
+  float fr, fg, fb;
+  switch (i) {
+    case 0: fr = RGB_max; fg = RGB_min + RGB_Adj; fb = RGB_min; break;
+    case 1: fr = RGB_max - RGB_Adj; fg = RGB_max; fb = RGB_min; break;
+    case 2: fr = RGB_min; fg = RGB_max; fb = RGB_min + RGB_Adj; break;
+    case 3: fr = RGB_min; fg = RGB_max - RGB_Adj; fb = RGB_max; break;
+    case 4: fr = RGB_min + RGB_Adj; fg = RGB_min; fb = RGB_max; break;
+    default: fr = RGB_max; fg = RGB_min; fb = RGB_max - RGB_Adj; break;
+  }
+  /* float -> unsigned char truncates; out-of-range values are undefined behaviour in the reference (negative hue):
+   * defined here as clamping */
+  const float v3[3] = {fr, fg, fb};
+  unsigned char o[3];
+  for (int k = 0; k < 3; ++k) {
+    float c = v3[k];
+    if (c < 0.f) c = 0.f;
+    if (c > 255.f) c = 255.f;
+    o[k] = (unsigned char)(int)c;
+  }
+  *r = o[0]; *g = o[1]; *b = o[2];
+}
+
+void ilcc2o_project_points(const void* points, int64_t n, int32_t step, int32_t ox, int32_t oy, int32_t oz, int32_t oi,
+                           const double T[16], const double cam[4], int32_t width, int32_t height, double dist,
+                           double inten_low, double inten_high, const uint8_t* image_bgr, int32_t* pix, uint8_t* rgbv) {
+  const unsigned char* base = (const unsigned char*)points;
+  for (int64_t i = 0; i < n; ++i) {
+    float x, y, z, in;
+    memcpy(&x, base + i * step + ox, 4);
+    memcpy(&y, base + i * step + oy, 4);
+    memcpy(&z, base + i * step + oz, 4);
+    memcpy(&in, base + i * step + oi, 4);
+    const double X = x, Y = y, Z = z;
+    const double pcx = ((T[0] * X + T[1] * Y) + T[2] * Z) + T[3];
+    const double pcy = ((T[4] * X + T[5] * Y) + T[6] * Z) + T[7];
+    const double pcz = ((T[8] * X + T[9] * Y) + T[10] * Z) + T[11];
+    pix[2 * i] = pix[2 * i + 1] = -1;
+    rgbv[4 * i] = rgbv[4 * i + 1] = rgbv[4 * i + 2] = rgbv[4 * i + 3] = 0;
+    if (pcz < 0 || pcz > dist) continue;
+    const double u = cam[0] * (pcx / pcz) + cam[1], v = cam[2] * (pcy / pcz) + cam[3];
+    if (!(u > 0 && u < width && v > 0 && v < height)) continue;
+    const int px = (int)u, py = (int)v;
+    pix[2 * i] = px;
+    pix[2 * i + 1] = py;
+    rgbv[4 * i + 3] = 1;
+    if (image_bgr) {
+      const uint8_t* q = image_bgr + ((size_t)py * width + px) * 3;
+      rgbv[4 * i] = q[2];
+      rgbv[4 * i + 1] = q[1];
+      rgbv[4 * i + 2] = q[0];
+    } else {
+      const double h = ((double)in - inten_low) / (inten_high - inten_low) * 255;
+      hsv_to_rgb(h == h ? (int)h : 0, 100, 100, &rgbv[4 * i], &rgbv[4 * i + 1], &rgbv[4 * i + 2]);
+    }
+  }
+}

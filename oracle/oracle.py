@@ -114,6 +114,9 @@ def lib() -> C.CDLL:
         L.ilcc2o_solve_pnp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_double,
                                        C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(PnpSummary)]
         L.ilcc2o_compose_extrinsic.argtypes = [C.c_void_p] * 4
+        L.ilcc2o_project_points.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double,
+                                            C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -322,3 +325,16 @@ def read_lidar_corners(path: str, num: int) -> np.ndarray:
     """ImageCornersEst::read_lidar_corners (:281-299): whitespace-separated floats parsed as float32."""
     v = np.array(open(path).read().split()[: 3 * num], dtype=np.float32).reshape(-1, 3)
     return v.astype(np.float64)
+
+
+def project_points(points: np.ndarray, T_lidar2cam, camera, width, height, distance_valid=5.0, inten_low=0.0,
+                   inten_high=60.0, image_bgr=None):
+    """spaceToPlane + colouring (pcd2image.cpp:59-84 / rgblidar.cpp:53-73). Returns (pix (n,2) int32, rgbv (n,4) uint8)."""
+    n, step, ox, oy, oz, oi = _layout(points)
+    T, cam = np.ascontiguousarray(T_lidar2cam, np.float64), np.ascontiguousarray(camera, np.float64)
+    pix, rgbv = np.empty((n, 2), np.int32), np.empty((n, 4), np.uint8)
+    img = None if image_bgr is None else np.ascontiguousarray(image_bgr, np.uint8)
+    lib().ilcc2o_project_points(points.ctypes.data, n, step, ox, oy, oz, oi, T.ctypes.data, cam.ctypes.data, width, height,
+                                distance_valid, inten_low, inten_high, None if img is None else img.ctypes.data,
+                                pix.ctypes.data, rgbv.ctypes.data)
+    return pix, rgbv

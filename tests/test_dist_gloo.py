@@ -23,8 +23,11 @@ b, c = ldist.shard_range(F, world, rank)
 pts, clicks = synth.make_batch(c, start=b)
 st, corners = O.extract_batch(pts, clicks, flags=O.FLAG_AUTO, threads=1)
 all_c, all_s = ldist.allgather_corners(torch.from_numpy(corners), torch.from_numpy(st), world)
+uv = torch.from_numpy(synth.project_truth(synth.make_batch(c, start=b, want_truth=True)[2], start=b))
+all_uv = ldist.allgather_rows(uv, world)
 if rank == 0:
     np.save({out!r} + "_corners.npy", all_c.numpy()); np.save({out!r} + "_status.npy", all_s.numpy())
+    np.save({out!r} + "_uv.npy", all_uv.numpy())
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -48,3 +51,6 @@ def test_two_ranks_gather_equals_single_process(tmp_path, oracle):
     st, corners = oracle.extract_batch(pts, clicks, flags=oracle.FLAG_AUTO, threads=2)
     assert np.array_equal(np.load(out + "_status.npy"), st)
     assert np.array_equal(np.load(out + "_corners.npy"), corners, equal_nan=True)
+    # the camera-side rows of configs[4] (projected ground truth, per-frame Philox noise) gather in rank order too
+    gt = synth.make_batch(6, want_truth=True)[2]
+    assert np.array_equal(np.load(out + "_uv.npy"), synth.project_truth(gt))

@@ -167,3 +167,31 @@ def test_synthetic_frames_close_the_loop_to_a_planted_extrinsic(api, oracle, fix
     assert int(valid.sum().item()) >= 35 * (F - 4)
     # method accuracy against the planted pose (corners are mm-cm accurate; averaged over ~90 frames)
     assert rot_angle(T[:3, :3], G[:3, :3]) < 5e-3 and np.linalg.norm(T[:3, 3] - G[:3, 3]) < 1.5e-2
+
+
+def test_project_points_matches_oracle_bit_for_bit(api, oracle, bag_clouds, fixtures):
+    """spaceToPlane + colouring of pcd2image / rgblidar -- integer pixels and bytes, so exact."""
+    import torch
+    from lidar_camera_calibration_b200 import synth
+    T = np.asarray(fixtures["extrinsic_lidar2cam"])
+    cam = camera4(fixtures)
+    W, H = fixtures["yaml"]["width"], fixtures["yaml"]["height"]
+    img = np.random.default_rng(1).integers(0, 255, (H, W, 3), dtype=np.uint8)
+    pnp = api.PnpSolver()
+    clouds = [bag_clouds[1], np.ascontiguousarray(bag_clouds[3][:, [0, 1, 2, 4]])]
+    pts, _ = synth.make_batch(4)
+    pts = pts.reshape(-1, 4).copy()
+    pts[::50, 0] = np.nan
+    pts[1::50, 3] = -7.0      # negative hue: undefined in the reference, clamped here and in the oracle
+    clouds.append(pts)
+    for c in clouds:
+        for image in (None, img):
+            for dist in (5.0, 2.5):
+                pix_o, rgb_o = oracle.project_points(c, T, cam, W, H, distance_valid=dist, image_bgr=image)
+                pix, rgb = pnp.project_points(c, T, cam, W, H, distance_valid=dist, image_bgr=image)
+                assert np.array_equal(pix, pix_o) and np.array_equal(rgb, rgb_o)
+                d_img = torch.from_numpy(image).cuda() if image is not None else None
+                dpix, drgb = pnp.project_points(torch.from_numpy(c).cuda(), T, cam, W, H, distance_valid=dist, image_bgr=d_img)
+                torch.cuda.synchronize()
+                assert np.array_equal(dpix.cpu().numpy(), pix_o) and np.array_equal(drgb.cpu().numpy(), rgb_o)
+    assert rgb_o[:, 3].sum() > 1000

@@ -116,3 +116,30 @@ def test_pnp_ignores_masked_pairs_and_recovers_a_planted_pose(oracle):
     r, t, sm = oracle.solve_pnp(p3, p2, cam, valid=valid)
     assert sm["n_pairs"] == int(valid.sum())
     assert np.abs(r - r_true).max() < 1e-6 and np.abs(t - t_true).max() < 1e-6
+
+
+def test_project_points_oracle_is_literal(fixtures, oracle, bag_clouds):
+    """spaceToPlane + HSVtoRGB against a direct numpy transcription (ImageCornersEst.cpp:135-155, :372-428)."""
+    rec = bag_clouds[1]
+    T = np.asarray(fixtures["extrinsic_lidar2cam"])
+    K = np.asarray(fixtures["yaml"]["K"])
+    cam = np.array([K[0, 0], K[0, 2], K[1, 1], K[1, 2]])
+    W, H = fixtures["yaml"]["width"], fixtures["yaml"]["height"]
+    pix, rgbv = oracle.project_points(rec, T, cam, W, H)
+    P = rec[:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        u, v = cam[0] * (P[:, 0] / P[:, 2]) + cam[1], cam[2] * (P[:, 1] / P[:, 2]) + cam[3]
+    valid = ~((P[:, 2] < 0) | (P[:, 2] > 5.0)) & (u > 0) & (u < W) & (v > 0) & (v < H)
+    assert np.array_equal(rgbv[:, 3] == 1, valid) and 3000 < valid.sum() < 10000
+    assert np.all(pix[~valid] == -1)
+    assert np.abs(pix[valid, 0] - np.trunc(u[valid])).max() <= 1 and np.abs(pix[valid, 1] - np.trunc(v[valid])).max() <= 1
+    for i in np.flatnonzero(valid)[::97]:
+        h = int((float(rec[i, 4]) - 0.0) / 60.0 * 255)
+        mx, adj = np.float32(255.0), np.float32(255.0) * np.float32(h % 60) / np.float32(60.0)
+        r, g, b = {0: (mx, adj, 0), 1: (mx - adj, mx, 0), 2: (0, mx, adj), 3: (0, mx - adj, mx), 4: (adj, 0, mx)}.get(
+            h // 60, (mx, 0, mx - adj))
+        assert tuple(rgbv[i, :3]) == (int(r), int(g), int(b))
+    img = np.random.default_rng(0).integers(0, 255, (H, W, 3), dtype=np.uint8)
+    pix2, rgb2 = oracle.project_points(np.ascontiguousarray(rec[:, [0, 1, 2, 4]]), T, cam, W, H, image_bgr=img)
+    assert np.array_equal(pix2, pix)
+    assert np.array_equal(rgb2[valid][:, :3], img[pix[valid, 1], pix[valid, 0]][:, ::-1])

@@ -29,15 +29,30 @@ WANT = [
     "smsp__average_warps_issue_stalled_selected_per_issue_active.ratio",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__sass_average_data_bytes_per_sector_mem_global_op_ld.pct",
     "local_load", "local_store", "sm__cycles_elapsed.max", "sm__cycles_active.avg",
+    "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct", "l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct",
+    "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "lts__t_sector_hit_rate.pct", "launch__occupancy_limit_barriers",
 ]
 
 
-def main(rep, out=None):
+def main(rep, out=None, traffic_json=None):
+    """traffic_json: also write {kernel base name: {"dram_bytes": read+write, "time_us": ...}} for the longest launch
+    of every kernel (bench.py's roofline.traffic reads it)."""
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     lines = []
+    traffic = {}
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tmul = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "usecond": 1.0, "msecond": 1e3, "nsecond": 1e-3, "second": 1e6}
     for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        base = name.replace("void ", "").split("(")[0].split("<")[0].split("::")[-1].replace("_kernel", "")
+        i_t, i_r, i_w = hdr.index("gpu__time_duration.sum"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        t_us = float(r[i_t]) * tmul.get(units[i_t], 1.0)
+        byt = float(r[i_r]) * mult.get(units[i_r], 1.0) + float(r[i_w]) * mult.get(units[i_w], 1.0)
+        if base not in traffic or t_us > traffic[base]["time_us"]:
+            traffic[base] = {"dram_bytes": byt, "time_us": t_us, "kernel": name[:80]}
         lines.append(f"== {r[hdr.index('Kernel Name')][:70]}  grid {r[hdr.index('Grid Size')]} block {r[hdr.index('Block Size')]}")
         for w in WANT:
             for i, h in enumerate(hdr):
@@ -47,6 +62,9 @@ def main(rep, out=None):
     print(text)
     if out:
         open(out, "w").write(text + "\n")
+    if traffic_json:
+        import json
+        json.dump(traffic, open(traffic_json, "w"), indent=1)
 
 
 if __name__ == "__main__":
