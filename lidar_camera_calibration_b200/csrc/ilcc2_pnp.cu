@@ -567,47 +567,76 @@ __device__ __forceinline__ uchar4 hsv_to_rgb_100(int h) {  // HSVtoRGB(h, 100, 1
   return make_uchar4(cv8(r), cv8(g), cv8(b), 1);
 }
 
+struct ProjPoint {
+  float x, y, z, in;
+};
+
 template <int MODE>  // 0: packed 16-byte XYZI, 1: 32-byte records (x,y,z@0, intensity@16), 2: generic offsets
+__device__ __forceinline__ ProjPoint proj_load(const unsigned char* rec, const ProjParams& P) {
+  ProjPoint q;
+  if (MODE == 0) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(rec));
+    q.x = v.x; q.y = v.y; q.z = v.z; q.in = v.w;
+  } else if (MODE == 1) {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(rec));
+    q.x = a.x; q.y = a.y; q.z = a.z;
+    q.in = __ldcs(reinterpret_cast<const float*>(rec + 16));
+  } else {
+    q.x = *reinterpret_cast<const float*>(rec + P.ox);
+    q.y = *reinterpret_cast<const float*>(rec + P.oy);
+    q.z = *reinterpret_cast<const float*>(rec + P.oz);
+    q.in = *reinterpret_cast<const float*>(rec + P.oi);
+  }
+  return q;
+}
+
+__device__ __forceinline__ void proj_one(const ProjPoint& q, const ProjParams& P, const unsigned char* __restrict__ image,
+                                         int2& px, uchar4& c) {
+  const double X = (double)q.x, Y = (double)q.y, Z = (double)q.z;
+  px = make_int2(-1, -1);
+  c = make_uchar4(0, 0, 0, 0);
+  const double pcz = ((P.R[6] * X + P.R[7] * Y) + P.R[8] * Z) + P.t[2];  // Eigen: m_R * P_w + m_t
+  if (pcz < 0.0 || pcz > P.dist || pcz != pcz) return;
+  const double pcx = ((P.R[0] * X + P.R[1] * Y) + P.R[2] * Z) + P.t[0];
+  const double pcy = ((P.R[3] * X + P.R[4] * Y) + P.R[5] * Z) + P.t[1];
+  const double u = P.fx * (pcx / pcz) + P.cx, v = P.fy * (pcy / pcz) + P.cy;
+  if (u > 0.0 && u < (double)P.width && v > 0.0 && v < (double)P.height) {
+    px = make_int2((int)u, (int)v);
+    if (image) {
+      const unsigned char* g = image + ((size_t)px.y * P.width + px.x) * 3;  // bgr8
+      c = make_uchar4(g[2], g[1], g[0], 1);
+    } else {
+      const double h = ((double)q.in - P.inten_low) / (P.inten_high - P.inten_low) * 255.0;
+      c = hsv_to_rgb_100(h == h ? (int)h : 0);
+    }
+  }
+}
+
+// four independent points per thread and iteration: the loads are issued before any of the arithmetic
+template <int MODE>
 __global__ void __launch_bounds__(256) project_points_kernel(const unsigned char* __restrict__ pts, long long n,
                                                              const ProjParams P, const unsigned char* __restrict__ image,
                                                              int2* __restrict__ pix, uchar4* __restrict__ rgb) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float x, y, z, in;
-    const unsigned char* rec = pts + (size_t)i * P.step;
-    if (MODE == 0) {
-      const float4 v = __ldcs(reinterpret_cast<const float4*>(rec));
-      x = v.x; y = v.y; z = v.z; in = v.w;
-    } else if (MODE == 1) {
-      const float4 a = __ldcs(reinterpret_cast<const float4*>(rec));
-      x = a.x; y = a.y; z = a.z;
-      in = __ldcs(reinterpret_cast<const float*>(rec + 16));
-    } else {
-      x = *reinterpret_cast<const float*>(rec + P.ox);
-      y = *reinterpret_cast<const float*>(rec + P.oy);
-      z = *reinterpret_cast<const float*>(rec + P.oz);
-      in = *reinterpret_cast<const float*>(rec + P.oi);
+  constexpr int U = 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
+    ProjPoint q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n) q[u] = proj_load<MODE>(pts + (size_t)i * P.step, P);
     }
-    const double X = (double)x, Y = (double)y, Z = (double)z;
-    const double pcx = ((P.R[0] * X + P.R[1] * Y) + P.R[2] * Z) + P.t[0];  // Eigen: m_R * P_w + m_t
-    const double pcy = ((P.R[3] * X + P.R[4] * Y) + P.R[5] * Z) + P.t[1];
-    const double pcz = ((P.R[6] * X + P.R[7] * Y) + P.R[8] * Z) + P.t[2];
-    int2 px = make_int2(-1, -1);
-    uchar4 c = make_uchar4(0, 0, 0, 0);
-    if (!(pcz < 0.0 || pcz > P.dist)) {
-      const double u = P.fx * (pcx / pcz) + P.cx, v = P.fy * (pcy / pcz) + P.cy;
-      if (u > 0.0 && u < (double)P.width && v > 0.0 && v < (double)P.height) {
-        px = make_int2((int)u, (int)v);
-        if (image) {
-          const unsigned char* q = image + ((size_t)px.y * P.width + px.x) * 3;  // bgr8
-          c = make_uchar4(q[2], q[1], q[0], 1);
-        } else {
-          const double h = ((double)in - P.inten_low) / (P.inten_high - P.inten_low) * 255.0;
-          c = hsv_to_rgb_100(h == h ? (int)h : 0);
-        }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n) {
+        int2 px;
+        uchar4 c;
+        proj_one(q[u], P, image, px, c);
+        __stcs(pix + i, px);
+        __stcs(rgb + i, c);
       }
     }
-    __stcs(pix + i, px);
-    __stcs(rgb + i, c);
   }
 }
 
