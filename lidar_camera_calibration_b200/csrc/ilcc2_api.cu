@@ -257,7 +257,11 @@ int ilcc2_create(const ilcc2_params* params, int device, int max_frames, int max
   A(dev_alloc(h, &w.fit_done, F));
   w.num_sms = prop.multiProcessorCount;
   w.fit_stride = (h->cap + 31) / 32 + 2ll * kFitGlobalTeam * h->cap;
-  A(dev_alloc(h, &w.fit_scratch, h->cap > kFitBitsCap ? F * (size_t)w.fit_stride : 1));
+  bool big_layout = h->cap > kFitBigFrame;
+  if (const char* e = getenv("ILCC2_FIT_LAYOUT")) big_layout = std::string(e) == "big";  // tests: force either K5 layout
+  w.fit_bits_cap = big_layout ? kFitBitsCapBig : kFitBitsCap;
+  w.fit_team_cap = big_layout ? kFitTeamCapBig : kFitTeamCap;
+  A(dev_alloc(h, &w.fit_scratch, h->cap > w.fit_bits_cap ? F * (size_t)w.fit_stride : 1));
   A(dev_alloc(h, &h->d_clicks, F * 3));
   A(dev_alloc(h, &h->d_flags, F));
   A(dev_alloc(h, &h->d_pdelta, F));
@@ -487,7 +491,7 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
     if (n_chunks == 1) CU_TRY(h, stage_done(4));
     launch_board_fit(w, h->dp, cs);
     if (n_chunks == 1) CU_TRY(h, stage_done(5));
-    h->launches += kStages + 1 + (h->cap > kFitBitsCap ? 1 : 0) + (h->cap > kClusterSmemPts ? 1 : 0);
+    h->launches += kStages + 1 + (h->cap > h->ws.fit_bits_cap ? 1 : 0) + (h->cap > kClusterSmemPts ? 1 : 0);
   }
   if (n_chunks > 1) {  // join the work streams back into the caller's stream
     for (int i = 0; i < ilcc2_handle::kWorkStreams; ++i) {

@@ -50,6 +50,11 @@ constexpr int kFitGlobalTeam = 2;     // team size of the global-memory instanti
 // depend on T and most of the SM's 256 KB stay L1 for the points.  Frames with more points are evaluated in chunks.
 constexpr int kFitTeamCap = FIT_TEAM_CAP;
 constexpr int kFitBitsCap = 8192;      // K5: colour bits kept in shared memory; larger frames take the global-memory path
+// Handles created for big frames (max_points_per_frame > kFitBigFrame, e.g. the 64 x 2048 HDL-64-like clouds whose
+// boards hold 10-14 k optimiser points) use a larger shared-memory layout instead: 4 KB of colour bits + 32 KB of lists.
+constexpr int kFitBigFrame = 65536;
+constexpr int kFitTeamCapBig = 16384;
+constexpr int kFitBitsCapBig = 32768;
 constexpr int kRndTable = 8192;       // PCL RANSAC draw table length
 
 // Everything a launch needs; passed by value.
@@ -84,6 +89,8 @@ struct Workspace {
   int* opt_count;              // [F]
   int* fit_order;              // [F] block index -> frame for K5 (work-balanced order)
   int* fit_done;               // [F] K5 with one CTA per hypothesis: CTAs of the frame that have finished
+  int fit_bits_cap;            // K5 shared-memory layout of this handle: colour-bit capacity (points) ...
+  int fit_team_cap;            // ... and points per chunk of a solve (list entries per team)
   int num_sms;
   uint32_t* fit_scratch;       // [F][fit_stride] K5 global-memory path: colour bits + two index lists
   long long fit_stride;
@@ -101,7 +108,7 @@ void launch_pca_gray(const Workspace& w, const DevParams& p, cudaStream_t s);
 void launch_board_fit(const Workspace& w, const DevParams& p, cudaStream_t s);
 cudaError_t configure_kernels();
 size_t cluster_smem_bytes();
-size_t fit_smem_bytes(int team);
+size_t fit_smem_bytes(const Workspace& w);
 int fit_team_size(int frames, int num_sms);
 
 }  // namespace ilcc2

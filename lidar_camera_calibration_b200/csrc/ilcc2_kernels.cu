@@ -1280,6 +1280,7 @@ struct FitPts {
   const uint32_t* wbits;
   int n;
   float* timing; // debug builds (FIT_TIMING): kilo-cycles spent in evaluation / scalar solver
+  int bits_bytes; // shared-memory instantiation: size of the colour-bit region in front of the lists
   IdxT* list;    // this warp's list buffer: L1 grows up from 0, L2 grows down from list_cap-1
   int list_cap;  // entries; also the chunk length (a chunk of list_cap points can never overflow it)
 };
@@ -1857,8 +1858,8 @@ __device__ FIT_SOLVE_ATTR int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp
     // LDS/STS with 32-bit addresses instead of generic loads/stores
     extern __shared__ unsigned char fit_sm[];
     wbits = reinterpret_cast<const uint32_t*>(fit_sm);
-    list = reinterpret_cast<IdxT*>(fit_sm + sizeof(uint32_t) * (kFitBitsCap / 32)) + (size_t)(threadIdx.x >> 5) * (kFitTeamCap / T);
-    list_cap = kFitTeamCap / T;
+    list_cap = Fp->list_cap;
+    list = reinterpret_cast<IdxT*>(fit_sm + Fp->bits_bytes) + (size_t)(threadIdx.x >> 5) * list_cap;
   }
   const int n = Fp->n;
   const VbModel M = *Mp;
@@ -2145,7 +2146,7 @@ __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) boa
   float* corners = w.corners + (size_t)f * p.ncorners * 3;
   const int st = d->status;
   const int n = w.opt_count[f];
-  if (st == ILCC2_OK && (n <= kFitBitsCap) != SMEM) return;  // the other instantiation owns this frame
+  if (st == ILCC2_OK && (n <= w.fit_bits_cap) != SMEM) return;  // the other instantiation owns this frame
   if (st != ILCC2_OK) {
     if (SMEM && hyp_cta == 0) {
       for (int i = tid; i < p.ncorners * 3; i += kThreads) corners[i] = NAN;
@@ -2165,15 +2166,17 @@ __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) boa
     // shared memory holds the two candidate lists (16-bit indices) and the colour bits; the points themselves are
     // read through L1 (a frame's optimiser points are ~20 KB and 7 frames share an SM), which keeps the CTA's
     // shared-memory footprint at 13 KB so that registers, not shared memory, bound the residency.
-    IdxT* lists = reinterpret_cast<IdxT*>(fit_sm + sizeof(uint32_t) * (kFitBitsCap / 32));
-    F.list = lists + (size_t)warp * (kFitTeamCap / T);
-    F.list_cap = kFitTeamCap / T;
+    F.bits_bytes = (int)sizeof(uint32_t) * (w.fit_bits_cap / 32);
+    IdxT* lists = reinterpret_cast<IdxT*>(fit_sm + F.bits_bytes);
+    F.list_cap = w.fit_team_cap / T;
+    F.list = lists + (size_t)warp * F.list_cap;
     F.yz = gyz;
     wbits = reinterpret_cast<uint32_t*>(fit_sm);
   } else {
     uint32_t* g = w.fit_scratch + (size_t)f * w.fit_stride;
     wbits = g;
     F.yz = gyz;
+    F.bits_bytes = 0;
     F.list = reinterpret_cast<IdxT*>(g + (w.cap + 31) / 32 + (size_t)(hyp_cta * T + warp) * w.cap);
     F.list_cap = w.cap;
   }
@@ -2303,9 +2306,8 @@ __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) boa
   }
 }
 
-size_t fit_smem_bytes(int team) {
-  (void)team;
-  return sizeof(uint32_t) * (kFitBitsCap / 32) + sizeof(uint16_t) * kFitTeamCap;
+size_t fit_smem_bytes(const Workspace& w) {
+  return sizeof(uint32_t) * (w.fit_bits_cap / 32) + sizeof(uint16_t) * w.fit_team_cap;
 }
 
 // Team size for a launch of `frames` frames: the largest T in {2, 4, 8} for which all 2 * frames CTAs are resident at
@@ -2324,7 +2326,7 @@ int fit_team_size(int frames, int num_sms) {
 
 template <int T>
 static void launch_fit_smem(const Workspace& w, const DevParams& p, cudaStream_t s) {
-  board_fit_kernel<true, T><<<2 * w.n_frames, 32 * T, fit_smem_bytes(T), s>>>(w, p);
+  board_fit_kernel<true, T><<<2 * w.n_frames, 32 * T, fit_smem_bytes(w), s>>>(w, p);
 }
 
 void launch_board_fit(const Workspace& w, const DevParams& p, cudaStream_t s) {
@@ -2335,20 +2337,24 @@ void launch_board_fit(const Workspace& w, const DevParams& p, cudaStream_t s) {
     case 4: launch_fit_smem<4>(w, p, s); break;
     default: launch_fit_smem<8>(w, p, s); break;
   }
-  if (w.cap > kFitBitsCap) board_fit_kernel<false, kFitGlobalTeam><<<2 * w.n_frames, 32 * kFitGlobalTeam, 0, s>>>(w, p);
+  if (w.cap > w.fit_bits_cap) board_fit_kernel<false, kFitGlobalTeam><<<2 * w.n_frames, 32 * kFitGlobalTeam, 0, s>>>(w, p);
 }
 
 cudaError_t configure_kernels() {
   cudaError_t e;
   e = cudaFuncSetAttribute(cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem_bytes());
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(board_fit_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem_bytes(1));
+  e = cudaFuncSetAttribute(board_fit_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(sizeof(uint32_t) * (kFitBitsCapBig / 32) + sizeof(uint16_t) * kFitTeamCapBig));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(board_fit_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem_bytes(2));
+  e = cudaFuncSetAttribute(board_fit_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(sizeof(uint32_t) * (kFitBitsCapBig / 32) + sizeof(uint16_t) * kFitTeamCapBig));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(board_fit_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem_bytes(4));
+  e = cudaFuncSetAttribute(board_fit_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(sizeof(uint32_t) * (kFitBitsCapBig / 32) + sizeof(uint16_t) * kFitTeamCapBig));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(board_fit_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem_bytes(8));
+  e = cudaFuncSetAttribute(board_fit_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(sizeof(uint32_t) * (kFitBitsCapBig / 32) + sizeof(uint16_t) * kFitTeamCapBig));
   return e;
 }
 

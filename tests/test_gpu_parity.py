@@ -175,10 +175,14 @@ def test_cpp_host_tool_writes_the_reference_output_files(api, bag_clouds, fixtur
     assert not (out / "pointgrey_lidar_4.txt").exists()
 
 
-def test_hdl64_like_frames_9x7_board(api, oracle):
+@pytest.mark.parametrize("layout", ["default", "small"])
+def test_hdl64_like_frames_9x7_board(api, oracle, layout, monkeypatch):
     """BASELINE.json config 4: 64 rings x 2048 azimuths, 9x7 board: ROI ~12-16 k points (> the shared-memory
-    clustering capacity -> global-memory path), ~10-14 k optimiser points (> the shared-memory bit capacity)."""
+    clustering capacity -> global-memory path of K2), ~10-14 k optimiser points: K5's large shared-memory layout by
+    default (handles for frames above 65536 points), its global-memory path when the small layout is forced."""
     from lidar_camera_calibration_b200 import synth
+    if layout == "small":
+        monkeypatch.setenv("ILCC2_FIT_LAYOUT", "small")
     F = 3
     pts, clicks, gt = synth.make_batch(F, scene=synth.SCENE_HDL64, want_truth=True)
     p_g = api.default_params(cells_x=8, cells_y=10)
@@ -193,7 +197,7 @@ def test_hdl64_like_frames_9x7_board(api, oracle):
         assert np.array_equal(ex.fetch_indices(f, 0), roi_o)
         assert np.array_equal(ex.fetch_indices(f, 1), clu_o)
         assert np.array_equal(ex.fetch_indices(f, 2), brd_o)
-        assert np.array_equal(diags[f]["pca"], d_o["pca"]) and diags[f]["n_opt"] == d_o["n_opt"] > 8192
+        assert np.array_equal(diags[f]["pca"], d_o["pca"]) and diags[f]["n_opt"] == d_o["n_opt"] > 8192  # > small layout
         assert np.linalg.norm(corners[f].astype(np.float64) - c_o, axis=1).max() <= TOL_CORNER_M
 
 
