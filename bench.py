@@ -207,6 +207,8 @@ def main():
     ap.add_argument("--cpu-sample-frames", type=int, default=256)
     ap.add_argument("--ref-sample-frames", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
+                    help="multi-GPU exchange: auto = fused into K5 (multicast if available, else peer stores), nccl = all_gather")
     ap.add_argument("--watchdog-s", type=int, default=900, help="dump all stacks and exit if the run exceeds this")
     args = ap.parse_args()
     import faulthandler
@@ -237,9 +239,31 @@ def main():
     h_status = torch.empty((F,), dtype=torch.int32).pin_memory()
     stream = torch.cuda.current_stream(dev)
 
+    # multi-GPU exchange: K5 stores the corners straight into every rank's gather buffer over NVLink (one barrier per
+    # step, no data-path collective); NCCL all-gather when symmetric memory is not available (--gather nccl forces it)
+    fused = None
+    if world > 1 and args.gather != "nccl":
+        try:
+            fused = ldist.FusedGather(ex, F, ncorn, rank, world, dev, use_multicast=(args.gather != "peer"))
+            g_corners, g_status = fused.corners, fused.status
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] fused gather unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
+            fused = None
+    if world > 1:
+        flag = torch.tensor([1 if fused is not None else 0], device=dev)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        if int(flag.item()) == 0 and fused is not None:
+            fused.close()
+            fused = None
+            g_corners = torch.empty((world * F, ncorn, 3), dtype=torch.float32, device=dev)
+            g_status = torch.empty((world * F,), dtype=torch.int32, device=dev)
+
     def step_device():
         ex.extract_torch(d_pts, d_clicks, d_corners, d_status, flags=api.FLAG_AUTO, stream=stream)
-        if world > 1:
+        if fused is not None:
+            fused.barrier()
+        elif world > 1:
             ldist.allgather_corners(d_corners, d_status, world, g_corners, g_status)
 
     def barrier():
@@ -289,7 +313,9 @@ def main():
     f0.record(stream)
     for _ in range(Ke):
         step_e2e()
-        if world > 1:
+        if fused is not None:
+            fused.barrier()
+        elif world > 1:
             ldist.allgather_corners(d_corners, d_status, world, g_corners, g_status)
     f1.record(stream)
     barrier()
@@ -303,6 +329,13 @@ def main():
     # ---- configs[4]: the PnP that follows the all-gather (not part of the frames/s figure) ----
     step_device()
     torch.cuda.synchronize(dev)
+    gather_ok = None
+    if world > 1:  # whichever exchange ran, every rank must hold what a plain NCCL all-gather delivers, bit for bit
+        ref_c, ref_s = ldist.allgather_corners(d_corners, d_status, world)
+        same = torch.equal(ref_s, g_status) and torch.equal(torch.nan_to_num(ref_c, nan=-1.0), torch.nan_to_num(g_corners, nan=-1.0))
+        t = torch.tensor([1 if same else 0], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
+        gather_ok = bool(t.item())
     pnp = pnp_leg(api, ldist, synth, torch, dev, rank, world, rank * F, gt,
                   g_corners if world > 1 else d_corners, g_status if world > 1 else d_status)
 
@@ -354,8 +387,10 @@ def main():
                                "7x5 board @0.15 m, colour phase auto (2 hypotheses x 2 solver phases per frame)",
                    "frames_per_gpu": F, "frames_total": world * F, "seed": synth.BASE_SEED,
                    "l2": f"inputs {F * N * 16 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
-                   "collective": "nccl all_gather of corners+status per step" if world > 1 else "none",
-                   "frames_ok": n_ok},
+                   "collective": ("none" if world == 1 else
+                                  f"fused into K5 ({fused.mode} into symmetric memory) + one signal-pad barrier per step"
+                                  if fused is not None else "nccl all_gather of corners+status per step"),
+                   "frames_ok": n_ok, "gather_equals_nccl_all_gather": gather_ok},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * N * 16 + F * 12),
                 "d2h_bytes_per_step": int(F * ncorn * 12 + F * 4), "steps": Ke, "ms_per_step": e2e_ms / Ke,

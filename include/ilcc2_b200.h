@@ -172,6 +172,16 @@ int64_t ilcc2_launch_count(const ilcc2_handle* h);
  * ostream precision of 6 significant digits (get_lidar_corners.cpp:27-36). */
 int ilcc2_save_corners2txt(const float* corners_xyz, int n_corners, const char* path);
 
+/* Multi-GPU: the all-gather of the per-frame corners fused into the kernel that produces them.
+ * After this call every ilcc2_extract_corners of the handle ALSO stores frame f's corners and status into each target at
+ * frame slot slot_base + f: corners_targets[t] is a device-accessible float[total_frames][n_corners][3],
+ * status_targets[t] an int32[total_frames].  Targets are peer-mapped buffers of the ranks of one NVLink/NVSwitch domain
+ * (n_targets = world size; e.g. torch symmetric memory or cudaIpc mappings) or one multicast (NVLS) mapping of such a
+ * buffer (n_targets = 1).  The caller separates producers and consumers with one barrier (no data-path collective).
+ * n_targets = 0 switches it off.  At most 8 targets. */
+int ilcc2_set_gather_targets(ilcc2_handle* h, int n_targets, float* const* corners_targets,
+                             int32_t* const* status_targets, int slot_base);
+
 /* Frame sharding across ranks (one process per GPU): contiguous blocks. */
 void ilcc2_shard_range(int n_frames, int world_size, int rank, int* begin, int* count);
 

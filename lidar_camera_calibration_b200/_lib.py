@@ -19,6 +19,7 @@ EXPORTS = [
     "ilcc2_pnp_create", "ilcc2_pnp_destroy", "ilcc2_pnp_last_error", "ilcc2_pnp_launch_count", "ilcc2_axis_roughly",
     "ilcc2_pnp_order_corners", "ilcc2_pnp_solve", "ilcc2_compose_extrinsic", "ilcc2_extrinsic2bin",
     "ilcc2_read_cam_corners", "ilcc2_read_lidar_corners", "ilcc2_read_camera_yaml", "ilcc2_project_points",
+    "ilcc2_set_gather_targets",
 ]
 
 
@@ -96,6 +97,8 @@ def load() -> C.CDLL:
     L.ilcc2_save_corners2txt.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
     L.ilcc2_shard_range.restype = None
     L.ilcc2_shard_range.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.ilcc2_set_gather_targets.restype = C.c_int
+    L.ilcc2_set_gather_targets.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]
     L.ilcc2_pnp_create.restype = C.c_int
     L.ilcc2_pnp_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     L.ilcc2_pnp_destroy.restype = C.c_int

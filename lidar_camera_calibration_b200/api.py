@@ -162,6 +162,15 @@ class CornerExtractor:
         return status, corners
 
     # ---- introspection of the last call ----
+    def set_gather_targets(self, corner_ptrs, status_ptrs, slot_base: int):
+        """ilcc2_set_gather_targets: K5 also stores every frame's corners / status into these device-accessible
+        buffers (peer mappings of the other ranks, or one multicast mapping) at frame slot slot_base + f."""
+        n = len(corner_ptrs)
+        assert n == len(status_ptrs)
+        ca = (C.c_void_p * max(n, 1))(*[int(p) for p in corner_ptrs])
+        sa = (C.c_void_p * max(n, 1))(*[int(p) for p in status_ptrs])
+        self._check(self._L.ilcc2_set_gather_targets(self._h, n, ca, sa, int(slot_base)))
+
     def fetch_indices(self, frame: int, which: int) -> np.ndarray:
         """which: 0 m_cloud_ROI, 1 chosen cluster, 2 m_cloud_chessboard -- original point indices of `frame`."""
         buf = np.empty(self.max_points, np.int32)

@@ -579,6 +579,25 @@ int ilcc2_stage_times(ilcc2_handle* h, float* ms_out, const char** names_out, in
   return kStages;
 }
 
+int ilcc2_set_gather_targets(ilcc2_handle* h, int n_targets, float* const* corners_targets,
+                             int32_t* const* status_targets, int slot_base) {
+  if (!h) return ILCC2_ERR_INVALID_ARGUMENT;
+  if (n_targets < 0 || n_targets > kMaxGatherTargets || slot_base < 0 ||
+      (n_targets > 0 && (!corners_targets || !status_targets)))
+    return fail(h, ILCC2_ERR_INVALID_ARGUMENT, "set_gather_targets: 0..%d targets, non-null pointer arrays", kMaxGatherTargets);
+  for (int i = 0; i < n_targets; ++i)
+    if (!corners_targets[i] || !status_targets[i])
+      return fail(h, ILCC2_ERR_INVALID_ARGUMENT, "set_gather_targets: target %d is null", i);
+  Workspace& w = h->ws;
+  w.n_targets = n_targets;
+  w.gather_slot_base = slot_base;
+  for (int i = 0; i < kMaxGatherTargets; ++i) {
+    w.gather_corners[i] = i < n_targets ? corners_targets[i] : nullptr;
+    w.gather_status[i] = i < n_targets ? status_targets[i] : nullptr;
+  }
+  return ILCC2_SUCCESS;
+}
+
 int64_t ilcc2_launch_count(const ilcc2_handle* h) { return h ? h->launches : 0; }
 
 int ilcc2_save_corners2txt(const float* corners_xyz, int n_corners, const char* path) {

@@ -57,6 +57,8 @@ constexpr int kFitTeamCapBig = 16384;
 constexpr int kFitBitsCapBig = 32768;
 constexpr int kRndTable = 8192;       // PCL RANSAC draw table length
 
+constexpr int kMaxGatherTargets = 8;   // ranks of one NVSwitch domain (or 1: a multicast mapping that reaches all of them)
+
 // Everything a launch needs; passed by value.
 struct Workspace {
   // caller input (device pointers)
@@ -99,6 +101,11 @@ struct Workspace {
   float* corners;              // [F][ncorners][3]
   int32_t* status;             // [F]
   ilcc2_diag* diag;            // [F] (always present internally)
+  // multi-GPU: K5 also stores corners / status into peer-mapped gather buffers (ilcc2_set_gather_targets)
+  int n_targets;               // 0 = off; else entries of gather_corners / gather_status in use
+  int gather_slot_base;        // frame f of this handle goes to slot gather_slot_base + f of every target
+  float* gather_corners[kMaxGatherTargets];
+  int32_t* gather_status[kMaxGatherTargets];
 };
 
 void launch_roi_filter(const Workspace& w, const DevParams& p, cudaStream_t s);

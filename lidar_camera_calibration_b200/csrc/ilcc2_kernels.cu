@@ -2126,6 +2126,17 @@ __global__ void __launch_bounds__(1024) fit_order_kernel(const Workspace w, int 
 #ifndef FIT_WARPS_PER_SM
 #define FIT_WARPS_PER_SM 16
 #endif
+// The all-gather of SURVEY.md 8(e) fused into the producer: besides the caller's own buffers, K5 stores a frame's
+// corners and status into every gather target -- peer-mapped buffers of the other ranks (plain stores over NVLink),
+// or ONE multicast mapping that NVSwitch fans out to all ranks (multimem.st is an ordinary st.sys on such an address).
+__device__ __forceinline__ void gather_store_corner(const Workspace& w, int f, int ncorners, int i, float v) {
+  const size_t at = (size_t)(w.gather_slot_base + f) * ncorners * 3 + i;
+  for (int t = 0; t < w.n_targets; ++t) w.gather_corners[t][at] = v;
+}
+__device__ __forceinline__ void gather_store_status(const Workspace& w, int f, int32_t st) {
+  for (int t = 0; t < w.n_targets; ++t) w.gather_status[t][w.gather_slot_base + f] = st;
+}
+
 template <bool SMEM, int T>
 __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) board_fit_kernel(const Workspace w, const DevParams p) {
   using IdxT = typename std::conditional<SMEM, uint16_t, uint32_t>::type;
@@ -2149,8 +2160,14 @@ __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) boa
   if (st == ILCC2_OK && (n <= w.fit_bits_cap) != SMEM) return;  // the other instantiation owns this frame
   if (st != ILCC2_OK) {
     if (SMEM && hyp_cta == 0) {
-      for (int i = tid; i < p.ncorners * 3; i += kThreads) corners[i] = NAN;
-      if (tid == 0) w.status[f] = st;
+      for (int i = tid; i < p.ncorners * 3; i += kThreads) {
+        corners[i] = NAN;
+        gather_store_corner(w, f, p.ncorners, i, NAN);
+      }
+      if (tid == 0) {
+        w.status[f] = st;
+        gather_store_status(w, f, st);
+      }
     }
     return;
   }
@@ -2299,10 +2316,12 @@ __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) boa
     corners[3 * k + 0] = r[0];
     corners[3 * k + 1] = r[1];
     corners[3 * k + 2] = r[2];
+    for (int c = 0; c < 3; ++c) gather_store_corner(w, f, p.ncorners, 3 * k + c, r[c]);
   }
   if (tid == 0) {
     d->hyp_chosen = chosen;
     w.status[f] = ILCC2_OK;
+    gather_store_status(w, f, ILCC2_OK);
   }
 }
 

@@ -60,3 +60,46 @@ def allgather_rows(x, world_size: int):
     out = torch.empty((world_size * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     dist.all_gather_into_tensor(out, x.contiguous())
     return out
+
+
+class FusedGather:
+    """The all-gather of the per-frame corners fused into the kernel that produces them.
+
+    Every rank owns one symmetric-memory buffer [world * F_local frames] (torch.distributed._symmetric_memory: the
+    allocations of all ranks are mapped into each other's address space over NVLink); K5 stores frame f of rank r into
+    slot r * F_local + f of EVERY rank's buffer (ilcc2_set_gather_targets) -- through the NVLS multicast mapping with
+    one store per value when the fabric offers it, else with one plain store per peer.  barrier() is the only
+    cross-rank operation of a step: a signal-pad barrier, no data moves through a collective.
+
+    Raises if symmetric memory cannot be set up; callers fall back to allgather_corners (NCCL)."""
+
+    def __init__(self, extractor, frames_local: int, n_corners: int, rank: int, world: int, device,
+                 use_multicast: bool = True):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank, self.F, self.ncorn = world, rank, frames_local, n_corners
+        total = world * frames_local
+        cbytes = total * n_corners * 3 * 4
+        self.buf = symm.empty((cbytes + total * 4,), dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.corners = self.buf[:cbytes].view(torch.float32).view(total, n_corners, 3)
+        self.status = self.buf[cbytes:].view(torch.int32)
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if use_multicast else 0
+        if mc:
+            self.mode = "nvls multicast store"
+            cptrs, sptrs = [mc], [mc + cbytes]
+        else:
+            self.mode = "peer stores"
+            cptrs = [int(p) for p in self.hdl.buffer_ptrs]
+            sptrs = [p + cbytes for p in cptrs]
+        extractor.set_gather_targets(cptrs, sptrs, rank * frames_local)
+        self._extractor = extractor
+        self.hdl.barrier(channel=0)
+
+    def barrier(self):
+        """All ranks' stores of this step are visible in every rank's buffer afterwards (runs on the current stream)."""
+        self.hdl.barrier(channel=0)
+
+    def close(self):
+        self._extractor.set_gather_targets([], [], 0)

@@ -279,3 +279,30 @@ def test_team_sizes_agree(api, oracle):
     ok = st_o == 0
     for c in (c2[:64], c4[:64], c8):
         assert np.abs(c[ok].astype(np.float64) - c_o[ok]).max() <= TOL_CORNER_M
+
+
+def test_gather_targets_receive_what_the_caller_receives(api):
+    """ilcc2_set_gather_targets on one device: two extra targets (stand-ins for peer mappings) at a slot offset get the
+    same corners / status as the caller's own buffers, including the NaN rows of failed frames."""
+    import torch
+    from lidar_camera_calibration_b200 import synth
+    F, base, total = 12, 5, 24
+    pts, clicks = synth.make_batch(F, start=700)
+    clicks = clicks.copy()
+    clicks[3] = [50.0, 50.0, 50.0]  # empty ROI -> status 1, NaN corners
+    ex = api.CornerExtractor(F, synth.VLP16.n_points)
+    tc = [torch.full((total, ex.n_corners, 3), -7.0, dtype=torch.float32, device="cuda") for _ in range(2)]
+    ts = [torch.full((total,), -7, dtype=torch.int32, device="cuda") for _ in range(2)]
+    ex.set_gather_targets([t.data_ptr() for t in tc], [t.data_ptr() for t in ts], base)
+    st, c = ex.extract_torch(torch.from_numpy(pts).cuda(), torch.from_numpy(clicks).cuda(), flags=api.FLAG_AUTO)
+    torch.cuda.synchronize()
+    assert int(st[3]) == 1
+    for t_c, t_s in zip(tc, ts):
+        assert torch.equal(t_s[base:base + F], st) and bool((t_s[:base] == -7).all()) and bool((t_s[base + F:] == -7).all())
+        assert torch.equal(torch.nan_to_num(t_c[base:base + F], nan=-1.0), torch.nan_to_num(c, nan=-1.0))
+        assert bool((t_c[:base] == -7).all()) and bool((t_c[base + F:] == -7).all())
+    ex.set_gather_targets([], [], 0)
+    ts[0].fill_(-7)
+    ex.extract_torch(torch.from_numpy(pts).cuda(), torch.from_numpy(clicks).cuda(), flags=api.FLAG_AUTO)
+    torch.cuda.synchronize()
+    assert bool((ts[0] == -7).all())
