@@ -1254,8 +1254,10 @@ void launch_pca_gray(const Workspace& w, const DevParams& p, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------
 // K5  board_fit: the virtual-chessboard pose optimisation (one ceres::Solve per phase in the reference).
-// One warp per (frame, colour hypothesis); both warps of a CTA share the frame's points in shared memory
-// (float2 y',z' + one colour bit per point).  A residual evaluation has two passes:
+// One CTA per (frame, colour hypothesis); the CTA is a team of T warps that share the solve (T = 8 / 4 / 2 / 1 chosen
+// per launch, see launch_board_fit).  The frame's points (float2 y',z') are read through L1, one colour bit per point
+// and the candidate lists live in shared memory.  A residual evaluation has two passes, each warp on its share of
+// the points:
 //   classify (fp32, every point): which virtual cell does the point fall in, with an error margin derived from
 //     a forward error bound of the fp32 arithmetic.  Points that are CERTAINLY inside a cell of their own
 //     colour (about 90 %) have a residual of exactly zero and are dropped; the others are compacted (ballot)
@@ -1264,9 +1266,12 @@ void launch_pca_gray(const Workspace& w, const DevParams& p, cudaStream_t s) {
 //   evaluate (fp64, listed points only, all lanes busy): the exact residual of Optimization.h:31-107, Huber
 //     cost, and -- when the step is accepted -- the 3-column Jacobian, J^T r and J^T J, from the SAME lists
 //     (Ceres evaluates the accepted point a second time; here nothing is recomputed for the dropped points).
-// Sums are lane-strided over the lists + xor butterfly: deterministic, but grouped differently from the CPU
-// oracle's sums (agreement ~1e-15 relative, see tests).  The 3x3 dogleg step (subspace dogleg,
-// Optimization.cpp:145-149) is computed redundantly by all lanes: no barrier inside a solve.
+// Sums are lane-strided over the lists + xor butterfly, then combined over the team's warps in fixed order through
+// one named barrier (team_sum): deterministic, but grouped differently from the CPU oracle's sums (agreement ~1e-15
+// relative, see tests).  The 3x3 dogleg step (subspace dogleg, Optimization.cpp:145-149) is computed redundantly by
+// all lanes of all warps from state kept in shared memory (ScalarWs): no exchange besides the sums.  The CTA of a
+// frame that finishes second picks the lower final cost and emits the corners (to the caller's buffers and to the
+// gather targets of the other ranks, if any).
 // ------------------------------------------------------------------------------------------------
 struct VbModel {
   int tlw;
@@ -1369,32 +1374,8 @@ __device__ __forceinline__ double fast_sqrt_pos(double a) {  // a > 0
   return g;
 }
 
-#ifdef FAST_DIV
-// Scalar-solver division / square root as short sequences (MUFU seed + Newton + one residual correction): the
-// results are within 1 ulp of the IEEE ones (usually equal).  Arguments outside the safe exponent range take the
-// IEEE path.  FAST_DIV=1 inlines them (independent divisions can overlap, larger image), FAST_DIV=2 keeps one copy.
-#if FAST_DIV == 2
-#define FAST_DIV_INLINE __noinline__
-#else
-#define FAST_DIV_INLINE __forceinline__
-#endif
-__device__ FAST_DIV_INLINE double ddiv(double a, double b) {
-  const double ab = fabs(b);
-  if (ab > 1e-280 && ab < 1e280 && fabs(a) < 1e280) {
-    const double r = fast_rcp(b);
-    const double q = a * r;
-    return fma(fma(-b, q, a), r, q);
-  }
-  return ddiv_ieee(a, b);
-}
-__device__ FAST_DIV_INLINE double dsqrt(double a) {
-  if (a > 1e-280 && a < 1e280) return fast_sqrt_pos(a);
-  return dsqrt_ieee(a);
-}
-#else
 __device__ __forceinline__ double ddiv(double a, double b) { return ddiv_ieee(a, b); }
 __device__ __forceinline__ double dsqrt(double a) { return dsqrt_ieee(a); }
-#endif
 
 // sincos() inlines a large slow path; keep one copy of it in the kernel
 __device__ __noinline__ void sincos_once(double x, double* s, double* c) { sincos(x, s, c); }
@@ -1431,10 +1412,12 @@ __device__ __forceinline__ void classify_pass(const float2* __restrict__ yz, con
     bool is1[U], is2[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      // no clamping: lanes at or beyond k1 read whatever follows (opt_yz is allocated 64 entries longer than the last
+      // frame needs, the colour bits are followed by the lists) and are masked out by `valid` below
       const int k = base + 32 * u + lane;
       const bool valid = k < k1;
-      const float2 q = __ldg(yz + (valid ? k : k0));
-      const unsigned wword = wbits[min(base + 32 * u, k1 - 1) >> 5];
+      const float2 q = __ldg(yz + k);
+      const unsigned wword = wbits[(base + 32 * u) >> 5];
       const float fi = fmaf(q.x, cg, fmaf(-q.y, sg, tyw));
       const float fj = fmaf(q.y, cg, fmaf(q.x, sg, tzh));
       const float ti = fi + kMagicF, tj = fj + kMagicF;
@@ -1566,9 +1549,6 @@ struct Dogleg {
 // ~8 KB per warp that competes with the frame's points for L1 (ncu: long-scoreboard stalls in the scalar code and
 // 85 MB of local-memory write-back per launch).  All lanes of a warp hold identical values, so they all store the
 // same data to the same address.
-#ifndef FIT_WS_LOCAL
-#define FIT_WS_SHARED 1
-#endif
 struct ScalarWs {
   Dogleg S;
   double Hs[6], gs[3], step[3];
@@ -1613,7 +1593,6 @@ __device__ bool tr2_eval(double a, double b, double dd, double g0, double g1, do
   const double ay = a + y, dy = dd + y;
   const double det = ay * dy - b * b;
   if (!(ay > 0.0) || !(det > 0.0)) return false;
-#ifndef NO_FAST_TR2
   if (det > 1e-280 && det < 1e280) {
     const double inv = fast_rcp(det);
     x[0] = -(dy * g0 - b * g1) * inv;
@@ -1622,7 +1601,6 @@ __device__ bool tr2_eval(double a, double b, double dd, double g0, double g1, do
     q = x[0] * ((dy * x[0] - b * x[1]) * inv) + x[1] * ((ay * x[1] - b * x[0]) * inv);
     return true;
   }
-#endif
   x[0] = ddiv(-(dy * g0 - b * g1), det);
   x[1] = ddiv(-(ay * g1 - b * g0), det);
   n2 = x[0] * x[0] + x[1] * x[1];
@@ -1648,9 +1626,7 @@ __device__ __noinline__ bool tr_boundary_2d(const double B[3], const double g[2]
   if (y < lo || y > hi) y = lo;
   double x[2] = {0.0, 0.0}, n2 = 0.0, q = 0.0;
   bool have = false;
-#ifndef NO_FAST_TR2
   const double inv_radius = (radius > 1e-280 && radius < 1e280) ? fast_rcp(radius) : ddiv(1.0, radius);  // Newton update only
-#endif
   double n_last = 0.0;
   for (int it = 0; it < 100; ++it) {
     if (!tr2_eval(a, b, dd, g[0], g[1], y, x, n2, q)) {
@@ -1660,20 +1636,12 @@ __device__ __noinline__ bool tr_boundary_2d(const double B[3], const double g[2]
       continue;
     }
     have = true;
-#ifndef NO_FAST_TR2
     const bool fast_ok = n2 > 1e-280 && n2 < 1e280 && fabs(q) > 1e-280 && fabs(q) < 1e280;
     const double n = fast_ok ? fast_sqrt_pos(n2) : dsqrt(n2);
     n_last = n;
     if (fabs(n - radius) <= 1e-14 * radius) break;
     if (n > radius) lo = y; else hi = y;
     double yn = fast_ok ? y + ((n - radius) * inv_radius) * (n2 * fast_rcp(q)) : y + ddiv(n - radius, radius) * ddiv(n2, q);
-#else
-    const double n = dsqrt(n2);
-    n_last = n;
-    if (fabs(n - radius) <= 1e-14 * radius) break;
-    if (n > radius) lo = y; else hi = y;
-    double yn = y + ddiv(n - radius, radius) * ddiv(n2, q);
-#endif
     if (!(yn > lo && yn < hi)) yn = 0.5 * (lo + hi);
     if (yn == y || !(hi > lo)) break;
     y = yn;
@@ -1840,13 +1808,8 @@ __device__ __forceinline__ void team_sum(double (&v)[NQ], double* slots /* [2][T
 // iteration counter and radius advance exactly as if the same candidate had been evaluated and rejected again.
 // Inlined into its single call site (the phase loop of board_fit_kernel): the model constants then come straight
 // from the kernel parameters and nothing is spilled around the call (ncu/ptxas: 216 B -> 0 B of spills, -8 % time).
-#ifdef FIT_SOLVE_NOINLINE
-#define FIT_SOLVE_ATTR __noinline__
-#else
-#define FIT_SOLVE_ATTR __forceinline__
-#endif
 template <typename IdxT, int T>
-__device__ FIT_SOLVE_ATTR int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, int oob_i, int max_iter, int lane,
+__device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, int oob_i, int max_iter, int lane,
                                      double* x, double* final_cost, int* iters_out, int* n_evals_io, double* slots,
                                      int* parity_io, ScalarWs* ws_shared) {
   const float2* __restrict__ yz = Fp->yz;
@@ -1868,13 +1831,7 @@ __device__ FIT_SOLVE_ATTR int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp
   int parity = *parity_io;
   const int team_cap = T * list_cap;  // points per chunk: each warp of the team classifies / evaluates its share
 
-#ifdef FIT_WS_SHARED
   ScalarWs& ws = *ws_shared;
-#else
-  ScalarWs ws_local;
-  ScalarWs& ws = ws_local;
-#endif
-#if defined(FIT_WS_SHARED) && !defined(FIT_WS_SMALL)
   double *xc = ws.xc, *cand = ws.cand, *g = ws.g, *H = ws.H, *scale = ws.scale, *xbest = ws.xbest;
   double &x_cost = ws.x_cost, &xnorm = ws.xnorm, &best_cost = ws.best_cost, &model_change = ws.model_change, &gmax = ws.gmax;
   for (int i = 0; i < 3; ++i) {
@@ -1884,12 +1841,6 @@ __device__ FIT_SOLVE_ATTR int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp
   }
   for (int i = 0; i < 6; ++i) H[i] = 0.0;
   x_cost = xnorm = best_cost = model_change = gmax = 0.0;
-#else
-  double xc[3] = {x[0], x[1], x[2]}, cand[3] = {x[0], x[1], x[2]};
-  double g[3] = {0, 0, 0}, H[6] = {0, 0, 0, 0, 0, 0}, scale[3] = {1, 1, 1};
-  double x_cost = 0.0, xnorm = 0.0, best_cost = 0.0, xbest[3] = {x[0], x[1], x[2]};
-  double model_change = 0.0, gmax = 0.0;
-#endif
   Dogleg& S = ws.S;
   S.radius = 1e4;
   S.mu = 1e-8;
@@ -2111,11 +2062,6 @@ __global__ void __launch_bounds__(1024) fit_order_kernel(const Workspace w, int 
       const int round = pos / num_sms, j = pos % num_sms;
       blk = round * num_sms + ((round & 1) ? num_sms - 1 - j : j);
     }
-#ifdef FIT_ORDER_IDENTITY
-    blk = f;
-#elif defined(FIT_ORDER_SORTED)
-    blk = pos;
-#endif
     w.fit_order[base + blk] = base + f;
   }
 }
