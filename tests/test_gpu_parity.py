@@ -306,3 +306,39 @@ def test_gather_targets_receive_what_the_caller_receives(api):
     ex.extract_torch(torch.from_numpy(pts).cuda(), torch.from_numpy(clicks).cuda(), flags=api.FLAG_AUTO)
     torch.cuda.synchronize()
     assert bool((ts[0] == -7).all())
+
+
+def test_batch_properties_at_bench_size(api):
+    """Size-independent properties on a 512-frame batch (what the oracle cannot check in seconds): run-to-run
+    determinism bit for bit, frames are independent (a permuted batch gives the permuted outputs, bit for bit -- also
+    across the K5 team sizes only to rounding, so the permutation keeps the batch size), the host-buffer path (chunked,
+    several team sizes) agrees with the device path to rounding, every OK frame's corners form the planted lattice
+    (neighbour spacing = grid_length within 1e-4 m); against the ground truth the median frame is mm-accurate (the
+    reference's optimiser -- and therefore the oracle and this path alike -- settles one square off on a minority of
+    frames, which its operator would see in the viewer; that is method accuracy, not parity)."""
+    import torch
+    from lidar_camera_calibration_b200 import synth
+    F = 512
+    pts, clicks, gt = synth.make_batch(F, start=9000, want_truth=True)
+    ex = api.CornerExtractor(F, synth.VLP16.n_points)
+    dp, dc = torch.from_numpy(pts).cuda(), torch.from_numpy(clicks).cuda()
+    st1, c1 = ex.extract_torch(dp, dc, flags=api.FLAG_AUTO)
+    st1, c1 = st1.clone(), c1.clone()
+    st2, c2 = ex.extract_torch(dp, dc, flags=api.FLAG_AUTO)
+    torch.cuda.synchronize()
+    assert torch.equal(st1, st2) and torch.equal(torch.nan_to_num(c1, nan=-1.0), torch.nan_to_num(c2, nan=-1.0))
+    perm = torch.randperm(F, generator=torch.Generator().manual_seed(1)).cuda()
+    st3, c3 = ex.extract_torch(dp[perm].contiguous(), dc[perm].contiguous(), flags=api.FLAG_AUTO)
+    torch.cuda.synchronize()
+    assert torch.equal(st3, st1[perm]) and torch.equal(torch.nan_to_num(c3, nan=-1.0), torch.nan_to_num(c1[perm], nan=-1.0))
+    st_h, c_h = ex.extract(pts, clicks, flags=api.FLAG_AUTO)
+    st_d, c_d = st1.cpu().numpy(), c1.cpu().numpy()
+    assert np.array_equal(st_h, st_d)
+    ok = st_d == 0
+    assert ok.sum() >= F - 8
+    assert np.abs(c_h[ok] - c_d[ok]).max() < 1e-6
+    lat = c_d[ok].reshape(-1, 5, 7, 3).astype(np.float64)
+    assert np.abs(np.linalg.norm(np.diff(lat, axis=2), axis=-1) - 0.15).max() < 1e-4
+    assert np.abs(np.linalg.norm(np.diff(lat, axis=1), axis=-1) - 0.15).max() < 1e-4
+    acc = np.array([synth.corner_set_distance(c_d[f], gt[f]) for f in np.flatnonzero(ok)])
+    assert np.median(acc) < 5e-3 and np.mean(acc < 2e-2) > 0.6
