@@ -1385,6 +1385,30 @@ __device__ __forceinline__ double huber_cost(const VbModel& M, double r) {
   return (sq > M.hb) ? 0.5 * (M.two_ha * r - M.hb) : 0.5 * sq;
 }
 
+// sm_100 packed fp32: two IEEE fp32 operations per instruction on a 64-bit register pair
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // fp32 classification of points [k0, k1) (k1 - k0 <= list_cap) at pose (c, s, ty, tz) -> lists L1 (up), L2 (down).
 //   fi = ((y c - z s) + ty + W g/2) / g  evaluated with two FMAs; forward error bound 5u(|y|+|z|+|t|)/g with
 //   u = 2^-24 (+1 rounding for the pre-scaled constants): 8u is used, times a safety factor 4 -> margin m.
@@ -1408,6 +1432,8 @@ __device__ __forceinline__ void classify_pass(const float2* __restrict__ yz, con
 #define CLS_UNROLL 2
 #endif
   constexpr int U = CLS_UNROLL;  // independent points per lane per iteration: the warp is latency-bound, not issue-bound
+  const f32x2 cg2 = pack2(cg, cg), sg2 = pack2(sg, sg), t2 = pack2(tyw, tzh), magic2 = pack2(kMagicF, kMagicF),
+              nmagic2 = pack2(-kMagicF, -kMagicF), nhalf2 = pack2(-Wh, -Hh);
   for (int base = k0; base < k1; base += 32 * U) {
     bool is1[U], is2[U];
 #pragma unroll
@@ -1418,15 +1444,32 @@ __device__ __forceinline__ void classify_pass(const float2* __restrict__ yz, con
       const bool valid = k < k1;
       const float2 q = __ldg(yz + k);
       const unsigned wword = wbits[(base + 32 * u) >> 5];
+#ifndef CLS_NO_F32X2
+      // Blackwell packed fp32 (FFMA2 / FADD2): the i and j coordinates go through identical operations, so every
+      // step is one instruction for both (bit-identical to the scalar sequence: each half is an IEEE fp32 op)
+      const f32x2 F = fma2(pack2(q.x, q.y), cg2, fma2(pack2(-q.y, q.x), sg2, t2));
+      const f32x2 Tm = add2(F, magic2);
+      const f32x2 D = sub2(F, add2(Tm, nmagic2));  // signed distance to the nearest integer
+      const f32x2 E0 = add2(F, nhalf2);            // (fi - Wh, fj - Hh)
+      float fi, fj, ti, tj, di, dj, ei, ej;
+      unpack2(F, fi, fj);
+      unpack2(Tm, ti, tj);
+      unpack2(D, di, dj);
+      unpack2(E0, ei, ej);
+      (void)fi;
+      (void)fj;
+      const float edge = fmaxf(fabsf(ei) - Wh, fabsf(ej) - Hh);  // < 0 inside the board, > 0 outside
+#else
       const float fi = fmaf(q.x, cg, fmaf(-q.y, sg, tyw));
       const float fj = fmaf(q.y, cg, fmaf(q.x, sg, tzh));
       const float ti = fi + kMagicF, tj = fj + kMagicF;
       const float di = fi - (ti - kMagicF), dj = fj - (tj - kMagicF);  // signed distance to the nearest integer
+      const float edge = fmaxf(fabsf(fi - Wh) - Wh, fabsf(fj - Hh) - Hh);  // < 0 inside the board, > 0 outside
+#endif
       // cell parity: parity(rint) ^ (d < 0)
       const unsigned par =
           (__float_as_uint(ti) ^ __float_as_uint(tj) ^ ((__float_as_uint(di) ^ __float_as_uint(dj)) >> 31)) & 1u;
       const bool interior = fminf(fabsf(di), fabsf(dj)) >= m;
-      const float edge = fmaxf(fabsf(fi - Wh) - Wh, fabsf(fj - Hh) - Hh);  // < 0 inside the board, > 0 outside
       const bool certain_in = interior && edge <= -m;
       const bool outb = edge >= m;
       const bool mism = ((((wword >> lane) ^ tlw ^ par) & 1u) != 0u);
