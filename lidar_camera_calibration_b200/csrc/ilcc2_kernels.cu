@@ -1589,6 +1589,7 @@ struct Dogleg {
   // values that only change when the Gauss-Newton step / subspace model is rebuilt, cached for the (many) rejected
   // iterations that reuse it: |gn|, and eigenvalues of sub_B and |sub_g| for the boundary problem
   double gnn, tb_l1, tb_l2, tb_gn;
+  double inv_diag[3];  // 1 / diag: x / diag is taken as x * inv_diag (<= 1.5 ulp instead of 0.5; one division per axis)
 };
 
 // Per-warp scratch of the scalar solver, kept in SHARED memory: the out-of-line dogleg routines take these by
@@ -1614,24 +1615,25 @@ __device__ __forceinline__ double quad3(const double H[6], const double u[3], co
   return u[0] * h0 + u[1] * h1 + u[2] * h2;
 }
 
+// 3x3 Cholesky solve; the three pivots are inverted once (3 divisions instead of 13)
 __device__ bool chol3_solve(const double A[6], const double b[3], double x[3]) {
   if (!(A[0] > 0.0)) return false;
-  const double l00 = dsqrt(A[0]);
-  const double l10 = ddiv(A[1], l00);
-  const double l20 = ddiv(A[2], l00);
+  const double i00 = ddiv(1.0, dsqrt(A[0]));
+  const double l10 = A[1] * i00;
+  const double l20 = A[2] * i00;
   double t = A[3] - l10 * l10;
   if (!(t > 0.0)) return false;
-  const double l11 = dsqrt(t);
-  const double l21 = ddiv(A[4] - l20 * l10, l11);
+  const double i11 = ddiv(1.0, dsqrt(t));
+  const double l21 = (A[4] - l20 * l10) * i11;
   t = A[5] - l20 * l20 - l21 * l21;
   if (!(t > 0.0)) return false;
-  const double l22 = dsqrt(t);
-  const double y0 = ddiv(b[0], l00);
-  const double y1 = ddiv(b[1] - l10 * y0, l11);
-  const double y2 = ddiv(b[2] - l20 * y0 - l21 * y1, l22);
-  x[2] = ddiv(y2, l22);
-  x[1] = ddiv(y1 - l21 * x[2], l11);
-  x[0] = ddiv(y0 - l10 * x[1] - l20 * x[2], l00);
+  const double i22 = ddiv(1.0, dsqrt(t));
+  const double y0 = b[0] * i00;
+  const double y1 = (b[1] - l10 * y0) * i11;
+  const double y2 = (b[2] - l20 * y0 - l21 * y1) * i22;
+  x[2] = y2 * i22;
+  x[1] = (y1 - l21 * x[2]) * i11;
+  x[0] = (y0 - l10 * x[1] - l20 * x[2]) * i00;
   return isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]);
 }
 
@@ -1703,12 +1705,15 @@ __device__ __noinline__ bool tr_boundary_2d(const double B[3], const double g[2]
 __device__ void dogleg_traditional(Dogleg& S, double step[3]) {
   const double gnorm = norm3(S.grad), gnn = S.gnn;
   if (gnn <= S.radius) {
-    for (int i = 0; i < 3; ++i) step[i] = ddiv(S.gn[i], S.diag[i]);
+    for (int i = 0; i < 3; ++i) step[i] = S.gn[i] * S.inv_diag[i];
     S.step_norm = gnn;
     return;
   }
   if (gnorm * S.alpha >= S.radius) {
-    for (int i = 0; i < 3; ++i) step[i] = ddiv(-ddiv(S.radius, gnorm) * S.grad[i], S.diag[i]);
+    {
+      const double sc = -ddiv(S.radius, gnorm);
+      for (int i = 0; i < 3; ++i) step[i] = (sc * S.grad[i]) * S.inv_diag[i];
+    }
     S.step_norm = S.radius;
     return;
   }
@@ -1721,19 +1726,22 @@ __device__ void dogleg_traditional(Dogleg& S, double step[3]) {
   double dl[3];
   for (int i = 0; i < 3; ++i) dl[i] = (-S.alpha * (1.0 - beta)) * S.grad[i] + beta * S.gn[i];
   S.step_norm = norm3(dl);
-  for (int i = 0; i < 3; ++i) step[i] = ddiv(dl[i], S.diag[i]);
+  for (int i = 0; i < 3; ++i) step[i] = dl[i] * S.inv_diag[i];
 }
 
 __device__ void dogleg_subspace_step(Dogleg& S, double step[3]) {
   const double gnn = S.gnn;
   if (gnn <= S.radius) {
-    for (int i = 0; i < 3; ++i) step[i] = ddiv(S.gn[i], S.diag[i]);
+    for (int i = 0; i < 3; ++i) step[i] = S.gn[i] * S.inv_diag[i];
     S.step_norm = gnn;
     return;
   }
   if (S.sub1d) {
     const double gnorm = norm3(S.grad);
-    for (int i = 0; i < 3; ++i) step[i] = ddiv(-ddiv(S.radius, gnorm) * S.grad[i], S.diag[i]);
+    {
+      const double sc = -ddiv(S.radius, gnorm);
+      for (int i = 0; i < 3; ++i) step[i] = (sc * S.grad[i]) * S.inv_diag[i];
+    }
     S.step_norm = S.radius;
     return;
   }
@@ -1742,7 +1750,7 @@ __device__ void dogleg_subspace_step(Dogleg& S, double step[3]) {
     dogleg_traditional(S, step);
     return;
   }
-  for (int i = 0; i < 3; ++i) step[i] = ddiv(S.U[i][0] * m2[0] + S.U[i][1] * m2[1], S.diag[i]);
+  for (int i = 0; i < 3; ++i) step[i] = (S.U[i][0] * m2[0] + S.U[i][1] * m2[1]) * S.inv_diag[i];
   S.step_norm = S.radius;
 }
 
@@ -1758,10 +1766,11 @@ __device__ __noinline__ bool dogleg_compute_step(Dogleg& S, const double Hs[6], 
     if (v < 1e-6) v = 1e-6;
     if (v > 1e32) v = 1e32;
     S.diag[i] = dsqrt(v);
+    S.inv_diag[i] = ddiv(1.0, S.diag[i]);
   }
-  for (int i = 0; i < 3; ++i) S.grad[i] = ddiv(gs[i], S.diag[i]);
+  for (int i = 0; i < 3; ++i) S.grad[i] = gs[i] * S.inv_diag[i];
   double sg[3];
-  for (int i = 0; i < 3; ++i) sg[i] = ddiv(S.grad[i], S.diag[i]);
+  for (int i = 0; i < 3; ++i) sg[i] = S.grad[i] * S.inv_diag[i];
   const double jg2 = quad3(Hs, sg, sg);
   S.alpha = ddiv(S.grad[0] * S.grad[0] + S.grad[1] * S.grad[1] + S.grad[2] * S.grad[2], jg2);
   bool ok = false;
@@ -1787,8 +1796,9 @@ __device__ __noinline__ bool dogleg_compute_step(Dogleg& S, const double Hs[6], 
   const double na = gfirst ? n_g : n_n;
   if (!(na > 0.0)) return false;
   double u0[3], bp[3], A1[3];
+  const double inv_na = ddiv(1.0, na);
   for (int i = 0; i < 3; ++i) {
-    u0[i] = ddiv(gfirst ? S.grad[i] : S.gn[i], na);
+    u0[i] = (gfirst ? S.grad[i] : S.gn[i]) * inv_na;
     A1[i] = gfirst ? S.gn[i] : S.grad[i];
   }
   const double pr = A1[0] * u0[0] + A1[1] * u0[1] + A1[2] * u0[2];
@@ -1799,15 +1809,16 @@ __device__ __noinline__ bool dogleg_compute_step(Dogleg& S, const double Hs[6], 
   } else {
     S.sub1d = 0;
     double w0[3], w1[3];
+    const double inv_nb = ddiv(1.0, nb);
     for (int i = 0; i < 3; ++i) {
       S.U[i][0] = u0[i];
-      S.U[i][1] = ddiv(bp[i], nb);
+      S.U[i][1] = bp[i] * inv_nb;
     }
     S.sub_g[0] = S.U[0][0] * S.grad[0] + S.U[1][0] * S.grad[1] + S.U[2][0] * S.grad[2];
     S.sub_g[1] = S.U[0][1] * S.grad[0] + S.U[1][1] * S.grad[1] + S.U[2][1] * S.grad[2];
     for (int i = 0; i < 3; ++i) {
-      w0[i] = ddiv(S.U[i][0], S.diag[i]);
-      w1[i] = ddiv(S.U[i][1], S.diag[i]);
+      w0[i] = S.U[i][0] * S.inv_diag[i];
+      w1[i] = S.U[i][1] * S.inv_diag[i];
     }
     S.sub_B[0] = quad3(Hs, w0, w0);
     S.sub_B[1] = quad3(Hs, w0, w1);
@@ -1897,6 +1908,7 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
   S.step_norm = 0.0;
   S.gnn = 0.0;
   S.tb_l1 = S.tb_l2 = S.tb_gn = 0.0;
+  S.inv_diag[0] = S.inv_diag[1] = S.inv_diag[2] = 1.0;
   int iter = 0, invalid = 0, term = TERM_MAX_ITER, n_evals = 0;
   bool succ = true, first = true;
 #ifdef FIT_TIMING
