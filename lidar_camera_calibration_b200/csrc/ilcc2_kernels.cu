@@ -1434,15 +1434,26 @@ __device__ __forceinline__ void classify_pass(const float2* __restrict__ yz, con
   constexpr int U = CLS_UNROLL;  // independent points per lane per iteration: the warp is latency-bound, not issue-bound
   const f32x2 cg2 = pack2(cg, cg), sg2 = pack2(sg, sg), t2 = pack2(tyw, tzh), magic2 = pack2(kMagicF, kMagicF),
               nmagic2 = pack2(-kMagicF, -kMagicF), nhalf2 = pack2(-Wh, -Hh);
+  // software pipeline: the points of the next iteration are loaded before this iteration's arithmetic (the first
+  // FFMA2 otherwise waits ~7 % of the kernel's samples for its load).  No clamping anywhere: lanes at or beyond k1 read
+  // whatever follows (opt_yz is allocated 128 entries longer than the last frame needs, the colour bits are followed by
+  // the lists) and are masked out by `valid` below.
+  float2 qn[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) qn[u] = __ldg(yz + k0 + 32 * u + lane);
   for (int base = k0; base < k1; base += 32 * U) {
     bool is1[U], is2[U];
+    float2 qc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      // no clamping: lanes at or beyond k1 read whatever follows (opt_yz is allocated 64 entries longer than the last
-      // frame needs, the colour bits are followed by the lists) and are masked out by `valid` below
+      qc[u] = qn[u];
+      qn[u] = __ldg(yz + base + 32 * (U + u) + lane);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
       const int k = base + 32 * u + lane;
       const bool valid = k < k1;
-      const float2 q = __ldg(yz + k);
+      const float2 q = qc[u];
       const unsigned wword = wbits[(base + 32 * u) >> 5];
 #ifndef CLS_NO_F32X2
       // Blackwell packed fp32 (FFMA2 / FADD2): the i and j coordinates go through identical operations, so every
@@ -1546,6 +1557,28 @@ __device__ __forceinline__ void list_pass(const float2* __restrict__ yz, const u
 #ifndef LIST_U
 #define LIST_U 1
 #endif
+#if LIST_U == 1
+  // L1: colour mismatch or not certain -> full residual.  Software pipeline: index, point and colour bit of the next
+  // iteration are fetched (shared-memory list -> L1 gather, a dependent chain) while this one is evaluated.
+  int kn = lane < n1 ? (int)list[lane] : 0;
+  float2 qn = __ldg(yz + kn);
+  unsigned wn = wbits[kn >> 5];
+  for (int e0 = 0; e0 < n1; e0 += 32) {
+    const bool act = e0 + lane < n1;
+    const int k = kn;
+    const float2 q = qn;
+    const unsigned wx = ((wn >> (k & 31)) & 1u) ^ (unsigned)M.tlw;
+    const int en = e0 + 32 + lane;
+    kn = en < n1 ? (int)list[en] : 0;
+    qn = __ldg(yz + kn);
+    wn = wbits[kn >> 5];
+    const double y = (double)q.x, z = (double)q.y;
+    double si, sj;
+    double r = vb_eval(M, oob, y, z, wx, c, s, ty, tz, si, sj);
+    if (!act) r = 0.0;
+    accumulate_point(M, want_jac, y, z, c, s, r, si, sj, a);
+  }
+#else
   for (int e0 = 0; e0 < n1; e0 += 32 * LIST_U) {  // L1: colour mismatch or not certain -> full residual
     double y[LIST_U], z[LIST_U], r[LIST_U], si[LIST_U], sj[LIST_U];
 #pragma unroll
@@ -1563,6 +1596,7 @@ __device__ __forceinline__ void list_pass(const float2* __restrict__ yz, const u
 #pragma unroll
     for (int u = 0; u < LIST_U; ++u) accumulate_point(M, want_jac, y[u], z[u], c, s, r[u], si[u], sj[u], a);
   }
+#endif
   if (oob) {
     for (int e0 = 0; e0 < n2; e0 += 32) {  // L2: certainly outside the board -> distance to the nearest edges
       const int e = e0 + lane;
