@@ -979,7 +979,16 @@ static int tr2_eval(double a, double b, double d, double g0, double g1, double y
   return 1;
 }
 
+/* test-only statistics: calls and Newton iterations of the boundary solver on the calling thread */
+static __thread long long g_tr2_calls = 0, g_tr2_iters = 0;
+void ilcc2o_tr2_stats(long long* calls, long long* iters, int reset) {
+  if (calls) *calls = g_tr2_calls;
+  if (iters) *iters = g_tr2_iters;
+  if (reset) g_tr2_calls = g_tr2_iters = 0;
+}
+
 int ilcc2o_tr_boundary_2d(const double B[3], const double g[2], double radius, double x_out[2]) {
+  g_tr2_calls++;
   const double a = B[0], b = B[1], d = B[2];
   const double tr = a + d, hd = 0.5 * (a - d);
   const double disc = sqrt(hd * hd + b * b);
@@ -997,6 +1006,7 @@ int ilcc2o_tr_boundary_2d(const double B[3], const double g[2], double radius, d
   double x[2] = {0, 0}, n2 = 0, q = 0;
   int have = 0;
   for (int it = 0; it < 100; ++it) {
+    g_tr2_iters++;
     if (!tr2_eval(a, b, d, g[0], g[1], y, x, &n2, &q)) {
       lo = y;
       y = 0.5 * (lo + hi);

@@ -161,6 +161,7 @@ void ilcc2o_compose_extrinsic(const double r[3], const double t[3], const double
 
 /* test-only: record the evaluation points of the solves run by the calling thread (4 doubles each: x[0..2], kind) */
 void ilcc2o_trace(double* buf, int cap);
+void ilcc2o_tr2_stats(long long* calls, long long* iters, int reset);
 int ilcc2o_trace_count(void);
 
 #ifdef __cplusplus
