@@ -117,3 +117,41 @@ def test_rosbag_reader_round_trip(tmp_path):
     assert pc.n_points == 5 and pc.point_step == 32 and pc.offsets_xyzi() == (0, 4, 8, 16)
     assert np.array_equal(pc.records_f32(), pts)
     assert np.array_equal(pc.packed_xyzi(), pts[:, [0, 1, 2, 4]])
+
+
+def test_calibration_host_entry_points_match_the_oracle_and_the_shipped_files(product_lib, oracle, fixtures, tmp_path):
+    """The host-only entry points around the PnP (rough axes, text readers, camera yaml, composing and writing the
+    extrinsic) need no GPU: they must agree with the oracle's restatement and with the reference's shipped artefacts."""
+    from lidar_camera_calibration_b200 import api
+    for cam in ("front", "car_left", "pointgrey", "left", "right", "back"):
+        assert np.array_equal(api.axis_roughly(cam), oracle.axis_roughly(cam))
+    with pytest.raises(api.Ilcc2Error):
+        api.axis_roughly("no_such_camera")
+    y = tmp_path / "pointgrey.yaml"
+    y.write_text(fixtures["yaml_text"])
+    K, cx, cy = api.read_camera_yaml(str(y))
+    assert np.array_equal(K, np.asarray(fixtures["yaml"]["K"])) and (cx, cy) == (7, 5)
+    for b in range(1, 7):
+        lp, cp = tmp_path / f"l{b}.txt", tmp_path / f"c{b}.txt"
+        lp.write_text(fixtures["lidar_corner_text"][str(b)])
+        cp.write_text(fixtures["cam_corner_text"][str(b)])
+        assert np.array_equal(api.read_lidar_corners(str(lp), 35), oracle.read_lidar_corners(str(lp), 35))
+        assert np.array_equal(api.read_cam_corners(str(cp), 35, 5), oracle.read_cam_corners(str(cp), 35, 5))
+    with pytest.raises(api.Ilcc2Error):
+        api.read_lidar_corners(str(tmp_path / "missing.txt"), 35)
+    # composing the shipped pose from the oracle's solution and writing it reproduces config/pointgrey.bin
+    Tax = oracle.axis_roughly("pointgrey")
+    P3, P2 = [], []
+    for b in range(1, 7):
+        p3 = oracle.read_lidar_corners(str(tmp_path / f"l{b}.txt"), 35) @ Tax[:3, :3].T + Tax[:3, 3]
+        P3.append(oracle.order_lidar(p3, 7, 5))
+        P2.append(oracle.order_cam(oracle.read_cam_corners(str(tmp_path / f"c{b}.txt"), 35, 5), 7, 5))
+    r, t, _ = oracle.solve_pnp(np.concatenate(P3), np.concatenate(P2), [K[0, 0], K[0, 2], K[1, 1], K[1, 2]])
+    T = api.compose_extrinsic(r, t, Tax)
+    assert np.allclose(T, oracle.compose_extrinsic(r, t, Tax), rtol=0, atol=1e-15)
+    out = tmp_path / "pose.bin"
+    api.extrinsic2bin(str(out), T)
+    got = np.fromfile(out, dtype="<f8")
+    ref = np.frombuffer(bytes.fromhex(fixtures["extrinsic_bin_hex"]), dtype="<f8")
+    assert got.shape == (16,) and np.abs(got - ref).max() < 1e-12
+    assert np.array_equal(got.reshape(4, 4).T, T)  # column-major on disk (Eigen::Matrix4d)
