@@ -250,7 +250,7 @@ int ilcc2_create(const ilcc2_params* params, int device, int max_frames, int max
   A(dev_alloc(h, &w.brd_count, F));
   A(dev_alloc(h, &w.tmp_idx, F * R));
   A(dev_alloc(h, &w.cl_scratch, need_global_cluster ? F * (size_t)w.cl_stride : 1));
-  A(dev_alloc(h, &w.opt_yz, F * R + 128));  // K5 classifies in groups of 64, one group prefetched, without clamping
+  A(dev_alloc(h, &w.opt_yz, F * R + 1024));  // K5 prefetches one team stride (<= 8 x 64 points) ahead without clamping
   A(dev_alloc(h, &w.opt_white, F * R));
   A(dev_alloc(h, &w.opt_count, F));
   A(dev_alloc(h, &w.fit_order, F));

@@ -115,7 +115,7 @@ void launch_pca_gray(const Workspace& w, const DevParams& p, cudaStream_t s);
 void launch_board_fit(const Workspace& w, const DevParams& p, cudaStream_t s);
 cudaError_t configure_kernels();
 size_t cluster_smem_bytes();
-size_t fit_smem_bytes(const Workspace& w);
+size_t fit_smem_bytes(const Workspace& w, int team);
 int fit_team_size(int frames, int num_sms);
 
 }  // namespace ilcc2

@@ -1279,6 +1279,9 @@ struct VbModel {
   float ymax_zmax;  // max|y'| + max|z'| over the frame's points (for the fp32 error bound)
 };
 
+// list entries per warp: the warps of a team take the 64-point groups of a chunk in turn
+__host__ __device__ inline int fit_list_cap(int team_cap, int team) { return ((team_cap / 64 + team - 1) / team) * 64; }
+
 template <typename IdxT>
 struct FitPts {
   const float2* yz;
@@ -1287,7 +1290,8 @@ struct FitPts {
   float* timing; // debug builds (FIT_TIMING): kilo-cycles spent in evaluation / scalar solver
   int bits_bytes; // shared-memory instantiation: size of the colour-bit region in front of the lists
   IdxT* list;    // this warp's list buffer: L1 grows up from 0, L2 grows down from list_cap-1
-  int list_cap;  // entries; also the chunk length (a chunk of list_cap points can never overflow it)
+  int list_cap;  // entries per warp: enough for the warp's share of a chunk (every T-th group of 64 points)
+  int team_cap;  // points per chunk
 };
 
 // exact residual of one point (Optimization.h:31-107) with the signs of its autodiff Jacobian, branch-free
@@ -1417,7 +1421,10 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
 template <typename IdxT>
 __device__ __forceinline__ void classify_pass(const float2* __restrict__ yz, const uint32_t* __restrict__ wbits,
                                               IdxT* list, int list_cap, const VbModel& M, bool oob, double c, double s,
-                                              double ty, double tz, int lane, int k0, int k1, int& n1, int& n2) {
+                                              double ty, double tz, int lane, int k0, int k1, int stride, int& n1,
+                                              int& n2) {
+  // points k0, k0 + stride, ... in groups of 32 * U: the warps of a team take the groups of a chunk in turn, so that
+  // each gets the same mix of the board's regions (balanced list lengths -> short waits at the team barrier)
   const float ig = (float)M.inv_g;
   const float cg = (float)c * ig, sg = (float)s * ig;
   const float tyw = (float)(ty + M.wg2) * ig, tzh = (float)(tz + M.hg2) * ig;
@@ -1441,13 +1448,13 @@ __device__ __forceinline__ void classify_pass(const float2* __restrict__ yz, con
   float2 qn[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) qn[u] = __ldg(yz + k0 + 32 * u + lane);
-  for (int base = k0; base < k1; base += 32 * U) {
+  for (int base = k0; base < k1; base += stride) {
     bool is1[U], is2[U];
     float2 qc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       qc[u] = qn[u];
-      qn[u] = __ldg(yz + base + 32 * (U + u) + lane);
+      qn[u] = __ldg(yz + base + stride + 32 * u + lane);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -1921,7 +1928,7 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
   const bool oob = oob_i != 0;
   const int wt = threadIdx.x >> 5;  // warp of the team
   int parity = *parity_io;
-  const int team_cap = T * list_cap;  // points per chunk: each warp of the team classifies / evaluates its share
+  const int team_cap = Fp->team_cap;  // points per chunk: each warp of the team classifies / evaluates its share
 
   ScalarWs& ws = *ws_shared;
   double *xc = ws.xc, *cand = ws.cand, *g = ws.g, *H = ws.H, *scale = ws.scale, *xbest = ws.xbest;
@@ -1963,11 +1970,10 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
 #ifdef FIT_TIMING
       const long long tc0 = clock64();
 #endif
-      // this warp's share of the chunk: a 32-aligned contiguous piece (may be empty)
+      // this warp's share of the chunk: every T-th group of 32 * CLS_UNROLL points
       const int k1 = min(k0 + team_cap, n);
-      const int piece = (((k1 - k0) + T - 1) / T + 31) & ~31;
-      const int ka = min(k0 + wt * piece, k1), kb = min(ka + piece, k1);
-      classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, cand[1], cand[2], lane, ka, kb, n1, n2);
+      classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, cand[1], cand[2], lane, k0 + wt * (32 * CLS_UNROLL), k1,
+                          T * 32 * CLS_UNROLL, n1, n2);
 #ifdef FIT_TIMING
       t_cls += clock64() - tc0;
 #endif
@@ -2005,9 +2011,8 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
         for (int k0 = 0; k0 < n; k0 += team_cap) {
           __syncwarp();
           const int k1 = min(k0 + team_cap, n);
-          const int piece = (((k1 - k0) + T - 1) / T + 31) & ~31;
-          const int ka = min(k0 + wt * piece, k1), kb = min(ka + piece, k1);
-          classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, xc[1], xc[2], lane, ka, kb, n1, n2);
+          classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, xc[1], xc[2], lane, k0 + wt * (32 * CLS_UNROLL), k1,
+                              T * 32 * CLS_UNROLL, n1, n2);
           list_pass<IdxT>(yz, wbits, list, list_cap, M, oob, true, cs, sn, xc[1], xc[2], lane, n1, n2, a);
         }
       }
@@ -2224,7 +2229,8 @@ __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) boa
     // shared-memory footprint at 13 KB so that registers, not shared memory, bound the residency.
     F.bits_bytes = (int)sizeof(uint32_t) * (w.fit_bits_cap / 32);
     IdxT* lists = reinterpret_cast<IdxT*>(fit_sm + F.bits_bytes);
-    F.list_cap = w.fit_team_cap / T;
+    F.team_cap = w.fit_team_cap;
+    F.list_cap = fit_list_cap(w.fit_team_cap, T);
     F.list = lists + (size_t)warp * F.list_cap;
     F.yz = gyz;
     wbits = reinterpret_cast<uint32_t*>(fit_sm);
@@ -2235,6 +2241,7 @@ __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) boa
     F.bits_bytes = 0;
     F.list = reinterpret_cast<IdxT*>(g + (w.cap + 31) / 32 + (size_t)(hyp_cta * T + warp) * w.cap);
     F.list_cap = w.cap;
+    F.team_cap = w.cap;
   }
   float ymax = 0.f, zmax = 0.f;
   for (int base = warp * 32; base < n; base += kThreads) {  // stage points; colour flags -> one bit per point
@@ -2364,8 +2371,8 @@ __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) boa
   }
 }
 
-size_t fit_smem_bytes(const Workspace& w) {
-  return sizeof(uint32_t) * (w.fit_bits_cap / 32) + sizeof(uint16_t) * w.fit_team_cap;
+size_t fit_smem_bytes(const Workspace& w, int team) {
+  return sizeof(uint32_t) * (w.fit_bits_cap / 32) + sizeof(uint16_t) * (size_t)team * fit_list_cap(w.fit_team_cap, team);
 }
 
 // Team size for a launch of `frames` frames: the largest T in {2, 4, 8} for which all 2 * frames CTAs are resident at
@@ -2384,7 +2391,7 @@ int fit_team_size(int frames, int num_sms) {
 
 template <int T>
 static void launch_fit_smem(const Workspace& w, const DevParams& p, cudaStream_t s) {
-  board_fit_kernel<true, T><<<2 * w.n_frames, 32 * T, fit_smem_bytes(w), s>>>(w, p);
+  board_fit_kernel<true, T><<<2 * w.n_frames, 32 * T, fit_smem_bytes(w, T), s>>>(w, p);
 }
 
 void launch_board_fit(const Workspace& w, const DevParams& p, cudaStream_t s) {
