@@ -4,8 +4,9 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank per GPU)
     python bench.py --impl reference ...                     (the CPU path on the box's host cores)
 
-A "step" is one pass of the whole hot path (K1 roi_filter .. K5 board_fit, + the NCCL all-gather of the corners
-when N>1) over one batch of --frames synthetic VLP-16 frames per GPU (BASELINE.json configs[2]; 8 ranks x 1024
+A "step" is one pass of the whole hot path (K1 roi_filter .. K5 board_fit, + the exchange of the corners between ranks
+when N>1: fused into K5 + one barrier, or an NCCL all-gather) over one batch of --frames synthetic VLP-16 frames per
+GPU (BASELINE.json configs[2]; 8 ranks x 1024
 frames = configs[4]).  Prints ONE JSON line (rank 0).
   value        frames/s with the batch already resident in HBM (CUDA events around exactly K steps, max over ranks)
   e2e          same metric through the C ABI with HOST buffers: pinned H2D of the batch + D2H of corners/status
@@ -167,6 +168,12 @@ def cpu_baseline(pts, clicks, sample_frames: int, threads: int):
     return n / dt, n, int((st == 0).sum())
 
 
+def workload_text(frames: int) -> str:
+    """config.workload: the same string on both arms (the driver compares them)."""
+    return (f"{frames} synthetic VLP-16 frames (16x1800 XYZI, 28800 pts, packed 16 B) per GPU per step, "
+            "7x5 board @0.15 m, colour phase auto (2 hypotheses x 2 solver phases per frame)")
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; the real thing cannot be built here) on all
     host threads, same metric / config; each step is a bounded sample of the workload."""
@@ -188,8 +195,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.frames} synthetic VLP-16 frames (16x1800 XYZI) per GPU, 7x5 board @0.15 m, "
-                               "colour phase auto", "frames_per_gpu": args.frames,
+        "config": {"workload": workload_text(args.frames), "frames_per_gpu": args.frames,
+                   "frames_total": args.gpus * args.frames, "seed": 20181203,
                    "reference_step": f"{sample} frames of that workload per step (bounded sample)"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} frames x {args.steps} steps, OpenMP over frames"},
@@ -383,9 +390,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{F} synthetic VLP-16 frames (16x1800 XYZI, 28800 pts, packed 16 B) per GPU per step, "
-                               "7x5 board @0.15 m, colour phase auto (2 hypotheses x 2 solver phases per frame)",
-                   "frames_per_gpu": F, "frames_total": world * F, "seed": synth.BASE_SEED,
+        "config": {"workload": workload_text(F), "frames_per_gpu": F, "frames_total": world * F, "seed": synth.BASE_SEED,
                    "l2": f"inputs {F * N * 16 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
                    "collective": ("none" if world == 1 else
                                   f"fused into K5 ({fused.mode} into symmetric memory) + one signal-pad barrier per step"
