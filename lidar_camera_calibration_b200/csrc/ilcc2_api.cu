@@ -237,7 +237,7 @@ int ilcc2_create(const ilcc2_params* params, int device, int max_frames, int max
   while (ts < 2 * h->cap) ts <<= 1;
   w.cl_ts = ts;
   w.cl_stride = 2ll * ts + 3ll * h->cap;
-  const bool need_global_cluster = h->cap > kClusterSmemPts;
+  const bool need_global_cluster = true;  // also the overflow path of the shared-memory tables
   cudaError_t ce = cudaSuccess;
   auto A = [&](cudaError_t r) { if (ce == cudaSuccess) ce = r; };
   A(dev_alloc(h, &w.roi_pts, F * R));
@@ -491,7 +491,7 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
     if (n_chunks == 1) CU_TRY(h, stage_done(4));
     launch_board_fit(w, h->dp, cs);
     if (n_chunks == 1) CU_TRY(h, stage_done(5));
-    h->launches += kStages + 1 + (h->cap > h->ws.fit_bits_cap ? 1 : 0) + (h->cap > kClusterSmemPts ? 1 : 0);
+    h->launches += kStages + 1 + (h->cap > h->ws.fit_bits_cap ? 1 : 0) + 1;
   }
   if (n_chunks > 1) {  // join the work streams back into the caller's stream
     for (int i = 0; i < ilcc2_handle::kWorkStreams; ++i) {

@@ -32,7 +32,8 @@ constexpr int kRoiThreads = 512;      // K1 CTA size for small batches (128 for 
 constexpr int kRoiUnroll = 4;         // K1 records per thread per tile
 constexpr int kClusterThreads = 256;  // K2 CTA size
 constexpr int kClusterSmemPts = 4096; // K2: frames with at most this many ROI points cluster in shared memory
-constexpr int kClusterSmemSlots = 8192;
+constexpr int kClusterSmemSlots = 4096;  // K2: hash slots (cells) in shared memory; 16-bit tables -> 66 KB per CTA, 3 CTAs per SM
+constexpr int kClusterMaxOcc = 3072;     // K2: more occupied cells than this -> the frame goes to the global-memory tables
 constexpr int kClusterBitmapRows = 2944; // K2: occupancy bitmap rows (ncy*ncz) that fit the shared-memory layout
 constexpr int kClusterQueue = 160;       // K2: per-warp queue of (cell, neighbour) pairs: 32 lanes x 5 dx
 constexpr int kPlaneThreads = 128;    // K3/K4 CTA size == canonical reduction width of their double sums

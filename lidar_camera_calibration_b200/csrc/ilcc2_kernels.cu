@@ -278,13 +278,29 @@ void launch_roi_filter(const Workspace& w, const DevParams& p, cudaStream_t s) {
 // tested with one load and the hash is only probed for cells that exist.  Larger frames use the same code on
 // a per-frame global scratch without the bitmap.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int uf_find(int* par, int x) {
-  volatile int* vp = par;
-  int cur = vp[x];
+// 16-bit tables in the shared-memory instantiation (point indices and slots are < 4096), 32-bit in the global one
+__device__ __forceinline__ int cas_idx(int* a, int cmp, int val) { return atomicCAS(a, cmp, val); }
+__device__ __forceinline__ int cas_idx(uint16_t* a, int cmp, int val) {
+  return (int)atomicCAS(reinterpret_cast<unsigned short*>(a), (unsigned short)cmp, (unsigned short)val);
+}
+__device__ __forceinline__ int exch_idx(int* a, int val) { return atomicExch(a, val); }
+__device__ __forceinline__ int exch_idx(uint16_t* a, int val) {  // no 16-bit atomicExch: CAS loop
+  int old = *reinterpret_cast<volatile uint16_t*>(a), assumed;
+  do {
+    assumed = old;
+    old = cas_idx(a, assumed, val);
+  } while (old != assumed);
+  return old;
+}
+
+template <typename ParT>
+__device__ __forceinline__ int uf_find(ParT* par, int x) {
+  volatile ParT* vp = par;
+  int cur = (int)vp[x];
   if (cur != x) {
     int prev = x, nx;
-    while (cur != (nx = vp[cur])) {
-      vp[prev] = nx;
+    while (cur != (nx = (int)vp[cur])) {
+      vp[prev] = (ParT)nx;
       prev = cur;
       cur = nx;
     }
@@ -292,7 +308,8 @@ __device__ __forceinline__ int uf_find(int* par, int x) {
   return cur;
 }
 
-__device__ __forceinline__ void uf_union(int* par, int a, int b) {
+template <typename ParT>
+__device__ __forceinline__ void uf_union(ParT* par, int a, int b) {
   int ra = uf_find(par, a), rb = uf_find(par, b);
   while (ra != rb) {
     if (ra < rb) {
@@ -300,7 +317,7 @@ __device__ __forceinline__ void uf_union(int* par, int a, int b) {
       ra = rb;
       rb = t;
     }
-    const int old = atomicCAS(&par[ra], ra, rb);  // link the larger root under the smaller
+    const int old = cas_idx(&par[ra], ra, rb);  // link the larger root under the smaller
     if (old == ra) break;
     ra = uf_find(par, old);
     rb = uf_find(par, rb);
@@ -316,8 +333,8 @@ __device__ __forceinline__ unsigned hash_cell(int k) {
 __device__ __forceinline__ int pack_cell(int x, int y, int z) { return x | (y << 10) | (z << 20); }
 
 template <typename NxtT>
-__device__ __forceinline__ void join_cells(const float4* __restrict__ P, const int* key, const int* head,
-                                           const NxtT* nxt, int* parent, int mask, int a, int kb, float tol2) {
+__device__ __forceinline__ void join_cells(const float4* __restrict__ P, const int* key, const NxtT* head,
+                                           const NxtT* nxt, NxtT* parent, int mask, int a, int kb, float tol2) {
   unsigned h = hash_cell(kb) & mask;
   for (;;) {
     const int kk = key[h];
@@ -325,7 +342,7 @@ __device__ __forceinline__ void join_cells(const float4* __restrict__ P, const i
     if (kk == -1) return;  // not occupied
     h = (h + 1) & mask;
   }
-  const int ha = head[a], hb = head[(int)h];
+  const int ha = (int)head[a], hb = (int)head[(int)h];
   if (uf_find(parent, ha) == uf_find(parent, hb)) return;
   constexpr int kEnd = (NxtT)(-1);
   for (int pa = ha; pa != kEnd; pa = (int)nxt[pa]) {
@@ -345,7 +362,7 @@ __constant__ signed char c_row_dy[13] = {0, 1, 2, -2, -1, 0, 1, 2, -2, -1, 0, 1,
 __constant__ signed char c_row_dz[13] = {0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2};
 
 template <bool SMEM>
-__global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspace w, const DevParams p) {
+__global__ void __launch_bounds__(kClusterThreads, SMEM ? 3 : 1) cluster_kernel(const Workspace w, const DevParams p) {
   constexpr int NT = kClusterThreads;
   using NxtT = typename std::conditional<SMEM, uint16_t, int>::type;
   constexpr int kEnd = (NxtT)(-1);
@@ -359,14 +376,17 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
   ilcc2_diag* d = w.diag + f;
   int* sel = w.sel_idx + (size_t)f * w.cap;
   const int M = w.roi_count[f];
-  if ((M <= kClusterSmemPts) != SMEM) return;  // the other instantiation owns this frame
+  // the shared-memory instantiation runs first and owns the frames that fit; it hands a frame over (sel_count = -1)
+  // when its hash table gets too full
+  if (SMEM ? (M > kClusterSmemPts) : (M <= kClusterSmemPts && w.sel_count[f] != -1)) return;
   if (M == 0) {
     if (tid == 0) w.sel_count[f] = 0;
     return;
   }
   int TS;
-  int *key, *head, *parent;
-  NxtT *nxt, *occ;
+  int* key;
+  NxtT *head, *parent, *nxt, *occ;
+  int* min_idx;  // step 3: lowest point index per component
   unsigned* bitmap = nullptr;
   unsigned* queue = nullptr;  // per-warp queue of (cell, neighbour) pairs
   int* qslot = nullptr;
@@ -375,26 +395,28 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
   if (SMEM) {
     TS = kClusterSmemSlots;
     key = sm;
-    head = key + TS;
+    head = reinterpret_cast<NxtT*>(key + TS);
     parent = head + TS;
-    nxt = reinterpret_cast<NxtT*>(parent + kClusterSmemPts);
+    nxt = parent + kClusterSmemPts;
     occ = nxt + kClusterSmemPts;
     bitmap = reinterpret_cast<unsigned*>(occ + kClusterSmemPts);
     queue = bitmap + kClusterBitmapRows + warp * kClusterQueue;
+    min_idx = reinterpret_cast<int*>(bitmap);  // bitmap + queues (>= kClusterSmemPts ints) are free by then
   } else {
     TS = w.cl_ts;
     int* g = w.cl_scratch + (size_t)f * w.cl_stride;
     key = g;
-    head = key + TS;
+    head = reinterpret_cast<NxtT*>(key + TS);
     parent = head + TS;
-    nxt = reinterpret_cast<NxtT*>(parent + w.cap);
+    nxt = parent + w.cap;
     occ = nxt + w.cap;
+    min_idx = reinterpret_cast<int*>(head);
     queue = s_queue_fallback + warp * kClusterQueue;
     qslot = s_queue_slot + warp * kClusterQueue;
   }
   for (int i = tid; i < TS; i += NT) {
     key[i] = -1;
-    head[i] = -1;
+    head[i] = (NxtT)kEnd;
   }
   if (use_bitmap)
     for (int i = tid; i < nrows; i += NT) bitmap[i] = 0u;
@@ -426,11 +448,15 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
       if (prev == k) break;
       h = (h + 1) & mask;
     }
-    nxt[i] = (NxtT)atomicExch(&head[h], i);
-    parent[i] = (int)h;  // slot for now
+    nxt[i] = (NxtT)exch_idx(&head[h], i);
+    parent[i] = (NxtT)h;  // slot for now
   }
   __syncthreads();
-  for (int i = tid; i < M; i += NT) parent[i] = head[parent[i]];  // same cell => same set
+  if (SMEM && s_nocc > kClusterMaxOcc) {  // lookups of absent cells need empty slots: leave the frame to the global tables
+    if (tid == 0) w.sel_count[f] = -1;
+    return;
+  }
+  for (int i = tid; i < M; i += NT) parent[i] = head[(int)parent[i]];  // same cell => same set
   __syncthreads();
   // 2. join neighbouring cells: G lanes per cell, lane r of a group owns row r of the forward (dy,dz) rows
   const int nocc = s_nocc;
@@ -511,8 +537,7 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
   }
   // 3. roots, sizes, lowest index per component (key/head tables are free now)
   NxtT* root = nxt;
-  int* size_of = key;
-  int* min_idx = head;
+  int* size_of = key;  // TS >= M entries
   NxtT* kept = occ;
   for (int i = tid; i < M; i += NT) {
     size_of[i] = 0;
@@ -540,7 +565,7 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
     return;
   }
   // 4. rank kept clusters: size descending, lowest first index first (PCL leaves ties unspecified)
-  int* rank_of = parent;  // indexed by root; parent[] is not needed once root[] is final
+  NxtT* rank_of = parent;  // indexed by root; parent[] is not needed once root[] is final
   for (int e = tid; e < nk; e += NT) {
     const int r = (int)kept[e];
     const int sz = size_of[r], mi = min_idx[r];
@@ -550,20 +575,20 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
       const int s2 = size_of[r2];
       if (s2 > sz || (s2 == sz && min_idx[r2] < mi)) ++rank;
     }
-    rank_of[r] = rank;
+    rank_of[r] = (NxtT)rank;
   }
   __syncthreads();
   if (tid == 0) {
     const int nn = (int)(w.nn_key[f] & 0xffffffffull);
     const int rn = (int)root[nn];
     const bool in = size_of[rn] >= p.min_cl && size_of[rn] <= p.max_cl;
-    int rank = in ? rank_of[rn] : 0;
+    int rank = in ? (int)rank_of[rn] : 0;
     const int delta = w.pdelta ? (int)w.pdelta[f] : 0;
     if (delta > 0) rank = min(rank + delta, nk - 1);
     if (delta < 0) rank = max(rank + delta, 0);
     int chosen = (int)kept[0];
     for (int j = 0; j < nk; ++j)
-      if (rank_of[(int)kept[j]] == rank) chosen = (int)kept[j];
+      if ((int)rank_of[(int)kept[j]] == rank) chosen = (int)kept[j];
     s_chosen_root = chosen;
     d->n_clusters = nk;
     d->click_in_cluster = in ? 1 : 0;
@@ -588,14 +613,16 @@ __global__ void __launch_bounds__(kClusterThreads) cluster_kernel(const Workspac
   (void)warp;
 }
 
-size_t cluster_smem_bytes() {
-  return sizeof(int) * (2 * kClusterSmemSlots + kClusterSmemPts) + sizeof(uint16_t) * 2 * kClusterSmemPts +
+size_t cluster_smem_bytes() {  // 66 KB: three CTAs per SM
+  static_assert(sizeof(unsigned) * (kClusterBitmapRows + (kClusterThreads / 32) * kClusterQueue) >= sizeof(int) * kClusterSmemPts,
+                "step 3 reuses the bitmap + queue region for one int per point");
+  return sizeof(int) * kClusterSmemSlots + sizeof(uint16_t) * (kClusterSmemSlots + 3 * kClusterSmemPts) +
          sizeof(unsigned) * (kClusterBitmapRows + (kClusterThreads / 32) * kClusterQueue);
 }
 
 void launch_cluster(const Workspace& w, const DevParams& p, cudaStream_t s) {
   cluster_kernel<true><<<w.n_frames, kClusterThreads, cluster_smem_bytes(), s>>>(w, p);
-  if (w.cap > kClusterSmemPts) cluster_kernel<false><<<w.n_frames, kClusterThreads, 0, s>>>(w, p);
+  cluster_kernel<false><<<w.n_frames, kClusterThreads, 0, s>>>(w, p);  // frames the first one could not take
 }
 
 // ------------------------------------------------------------------------------------------------

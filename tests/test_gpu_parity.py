@@ -342,3 +342,29 @@ def test_batch_properties_at_bench_size(api):
     assert np.abs(np.linalg.norm(np.diff(lat, axis=1), axis=-1) - 0.15).max() < 1e-4
     acc = np.array([synth.corner_set_distance(c_d[f], gt[f]) for f in np.flatnonzero(ok)])
     assert np.median(acc) < 5e-3 and np.mean(acc < 2e-2) > 0.6
+
+
+def test_sparse_roi_overflows_the_shared_memory_cell_table(api, oracle):
+    """K2 keeps 4096 hash slots in shared memory; a ROI whose points occupy more than 3072 cells (a sparse cloud: most
+    points alone in their cell) is handed over to the global-memory tables.  Clusters must not depend on the path."""
+    rng = np.random.default_rng(11)
+    F, N = 3, 12000
+    pts = np.empty((F, N, 4), np.float32)
+    clicks = np.zeros((F, 3), np.float32)
+    for f in range(F):
+        box = rng.uniform([-0.69, -1.29, -2.39], [1.29, 1.69, 1.59], (3700, 3))     # inside the ROI, sparse: ~3.6 k cells
+        blob = rng.normal(0.0, 0.05, (150 + 40 * f, 3)) + [0.3, 0.2, -0.4]          # one dense cluster near the click
+        far = rng.uniform(5.0, 9.0, (N - len(box) - len(blob), 3))                  # outside the ROI
+        xyz = np.concatenate([blob, box, far])
+        pts[f, :, :3] = xyz[rng.permutation(N)]
+        pts[f, :, 3] = rng.integers(0, 100, N)
+        clicks[f] = [0.3, 0.2, -0.4]
+    ex = api.CornerExtractor(F, N)
+    st, corners, diags = ex.extract(pts, clicks, flags=api.FLAG_AUTO, want_diag=True)
+    for f in range(F):
+        st_o, c_o, d_o, roi_o, clu_o, brd_o = oracle.extract_frame(pts[f], clicks[f], flags=oracle.FLAG_AUTO, want_indices=True)
+        assert 3072 < d_o["n_roi"] <= 4096
+        assert st[f] == st_o
+        for k in ("n_roi", "n_clusters", "click_in_cluster", "cluster_rank", "n_cluster_pts"):
+            assert diags[f][k] == d_o[k], (k, diags[f][k], d_o[k])
+        assert d_o["n_clusters"] >= 1 and np.array_equal(ex.fetch_indices(f, 1), clu_o)
