@@ -102,6 +102,18 @@ def test_calib_lidar_cam_host_tool_writes_the_shipped_extrinsic(api, fixtures, t
     assert got.shape == (16,) and np.abs(got - ref).max() < 1e-9
 
 
+def test_calib_node_on_the_reference_shaped_adaptor(api, fixtures, tmp_path):
+    """host/calib_lidar_cam_node.cpp: the reference node's main() against include/ilcc2_b200/Calibration.hpp."""
+    from lidar_camera_calibration_b200 import _lib
+    lay_out_package(fixtures, tmp_path)
+    tool = os.path.join(os.path.dirname(_lib.LIB_PATH), "host", "calib_lidar_cam_node")
+    out = subprocess.run([tool, str(tmp_path), "6"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    got = np.fromfile(tmp_path / "config" / "pointgrey.bin", dtype="<f8")
+    ref = np.frombuffer(bytes.fromhex(fixtures["extrinsic_bin_hex"]), dtype="<f8")
+    assert got.shape == (16,) and np.abs(got - ref).max() < 1e-9 and "24 iterations" in out.stdout
+
+
 def test_bundled_bags_recover_the_same_R_t_from_gpu_and_oracle_corners(api, oracle, bag_clouds, fixtures, tmp_path):
     """North star: corners from the CUDA path and from the CPU oracle, each pushed through the reference's own
     file contract (save_corners2txt -> read_lidar_corners) and the PnP, give the same R, t within 1e-3 rad / 1e-3 m
