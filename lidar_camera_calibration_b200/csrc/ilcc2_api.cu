@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -341,6 +342,8 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
     if (o < 0 || o % 4 != 0 || o + 4 > point_step) return fail(h, ILCC2_ERR_INVALID_ARGUMENT, "field offset %d invalid", o);
   const bool fast = (point_step == 16 && off_x == 0 && off_y == 4 && off_z == 8 && off_intensity == 12) ||
                     (point_step == 32 && off_x == 0 && off_y == 4 && off_z == 8 && off_intensity == 16);
+  if (fast && mem_kind == ILCC2_MEM_DEVICE && (reinterpret_cast<uintptr_t>(points) & 15u) != 0)
+    return fail(h, ILCC2_ERR_INVALID_ARGUMENT, "device point buffers of 16- / 32-byte records must be 16-byte aligned (128-bit loads)");
   long long total_points = 0;
   h->last_frame_off.clear();
   if (frame_offsets) {

@@ -15,6 +15,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -892,7 +893,8 @@ int ilcc2_project_points(ilcc2_pnp* h, const void* points, int64_t n_points, int
   if (!h) return ILCC2_ERR_INVALID_ARGUMENT;
   if (!points || !T_lidar2cam || !camera || !pix_xy_out || !rgbv_out || n_points < 1 || point_step < 16 || width < 1 ||
       height < 1 || off_x < 0 || off_y < 0 || off_z < 0 || off_intensity < 0 || off_x + 4 > point_step ||
-      off_y + 4 > point_step || off_z + 4 > point_step || off_intensity + 4 > point_step || (point_step & 3))
+      off_y + 4 > point_step || off_z + 4 > point_step || off_intensity + 4 > point_step || (point_step & 3) ||
+      ((off_x | off_y | off_z | off_intensity) & 3))
     return pfail(h, ILCC2_ERR_INVALID_ARGUMENT, "project_points: null or out-of-range argument");
   if (mem_kind != ILCC2_MEM_HOST && mem_kind != ILCC2_MEM_DEVICE)
     return pfail(h, ILCC2_ERR_INVALID_ARGUMENT, "mem_kind must be ILCC2_MEM_HOST or ILCC2_MEM_DEVICE");
@@ -926,8 +928,9 @@ int ilcc2_project_points(ilcc2_pnp* h, const void* points, int64_t n_points, int
   long long blocks = (n_points + threads - 1) / threads;
   const long long cap = 8ll * h->num_sms * 4;  // 8 resident CTAs per SM, 4 points per thread at full size
   if (blocks > cap) blocks = cap;
-  const bool packed = point_step == 16 && off_x == 0 && off_y == 4 && off_z == 8 && off_intensity == 12;
-  const bool pcl32 = point_step == 32 && off_x == 0 && off_y == 4 && off_z == 8 && off_intensity == 16;
+  const bool aligned16 = (reinterpret_cast<uintptr_t>(d_pts) & 15u) == 0;  // 128-bit loads; else the generic path
+  const bool packed = aligned16 && point_step == 16 && off_x == 0 && off_y == 4 && off_z == 8 && off_intensity == 12;
+  const bool pcl32 = aligned16 && point_step == 32 && off_x == 0 && off_y == 4 && off_z == 8 && off_intensity == 16;
   if (packed)
     project_points_kernel<0><<<(int)blocks, threads, 0, s>>>(d_pts, n_points, P, d_img, d_pix, d_rgb);
   else if (pcl32)
