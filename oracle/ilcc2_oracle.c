@@ -24,6 +24,22 @@
 #endif
 
 /* ------------------------------------------------------------------------------------------ */
+/* test-only restatement switches (ilcc2o_set_variant): each bit replaces ONE restatement choice */
+/* by its alternative so that tests/tools can measure how far the end result moves (DESIGN.md    */
+/* "deviation table").  0 = the choices documented in the header.  Not thread-local: set it      */
+/* before a batch, never during one.                                                             */
+/* ------------------------------------------------------------------------------------------ */
+static uint32_t g_variant = 0;
+static int g_extra_d_pairs = 0;   /* extra pairs of 'd' presses (each press toggles topleftWhite and re-optimises warm) */
+static int g_tr_perturb_ulps = 0; /* boundary-problem solution moved by this many ulps (sensitivity probe) */
+void ilcc2o_set_variant(uint32_t mask, int extra_d_pairs, int tr_perturb_ulps) {
+  g_variant = mask;
+  g_extra_d_pairs = extra_d_pairs < 0 ? 0 : extra_d_pairs;
+  g_tr_perturb_ulps = tr_perturb_ulps;
+}
+uint32_t ilcc2o_get_variant(void) { return g_variant; }
+
+/* ------------------------------------------------------------------------------------------ */
 /* canonical reduction                                                                        */
 /* ------------------------------------------------------------------------------------------ */
 /* Element k is added to partial sum k mod w (in increasing k); the w partial sums are combined by an xor
@@ -363,6 +379,102 @@ static void jacobi3d(const double A[6], double ev[3], double V[3][3]) {
 /* first inlier) and takes the smallest eigenvector from a double Jacobi solver; PCL accumulates */
 /* raw moments in float and uses a closed-form float eigen33.                                    */
 /* ------------------------------------------------------------------------------------------ */
+/* [UPSTREAM PCL 1.7] SampleConsensusModelPlane::optimizeModelCoefficients as PCL writes it: raw moments
+ * accumulated sequentially in fp32 (computeMeanAndCovarianceMatrix), covariance = E[xx] - E[x]E[x], smallest
+ * eigenvector by the closed-form pcl::eigen33 (computeRoots + row cross products), d = -n.c. */
+static void pcl_roots2_f32(float b, float c, float roots[3]) {
+  roots[0] = 0.0f;
+  float d = (float)(b * b - 4.0 * c);
+  if (d < 0.0f) d = 0.0f;
+  const float sd = sqrtf(d);
+  roots[2] = 0.5f * (b + sd);
+  roots[1] = 0.5f * (b - sd);
+}
+static void pcl_plane_refit_f32(const float* xyz, const int* inl, int ni, float out[4]) {
+  float a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < ni; ++k) {
+    const float* p = xyz + 3 * inl[k];
+    a[0] += p[0] * p[0];
+    a[1] += p[0] * p[1];
+    a[2] += p[0] * p[2];
+    a[3] += p[1] * p[1];
+    a[4] += p[1] * p[2];
+    a[5] += p[2] * p[2];
+    a[6] += p[0];
+    a[7] += p[1];
+    a[8] += p[2];
+  }
+  const float inv = 1.0f / (float)ni;
+  for (int q = 0; q < 9; ++q) a[q] *= inv;
+  float m[3][3];
+  m[0][0] = a[0] - a[6] * a[6];
+  m[0][1] = a[1] - a[6] * a[7];
+  m[0][2] = a[2] - a[6] * a[8];
+  m[1][1] = a[3] - a[7] * a[7];
+  m[1][2] = a[4] - a[7] * a[8];
+  m[2][2] = a[5] - a[8] * a[8];
+  m[1][0] = m[0][1]; m[2][0] = m[0][2]; m[2][1] = m[1][2];
+  float scale = 0.0f;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      if (fabsf(m[r][c]) > scale) scale = fabsf(m[r][c]);
+  if (scale <= FLT_MIN) scale = 1.0f;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) m[r][c] = m[r][c] / scale;
+  float roots[3];
+  {
+    const float c0 = m[0][0] * m[1][1] * m[2][2] + 2.0f * m[0][1] * m[0][2] * m[1][2] - m[0][0] * m[1][2] * m[1][2] -
+                     m[1][1] * m[0][2] * m[0][2] - m[2][2] * m[0][1] * m[0][1];
+    const float c1 = m[0][0] * m[1][1] - m[0][1] * m[0][1] + m[0][0] * m[2][2] - m[0][2] * m[0][2] + m[1][1] * m[2][2] -
+                     m[1][2] * m[1][2];
+    const float c2 = m[0][0] + m[1][1] + m[2][2];
+    if (fabsf(c0) < FLT_EPSILON) {
+      pcl_roots2_f32(c2, c1, roots);
+    } else {
+      const float s_inv3 = (float)(1.0 / 3.0), s_sqrt3 = sqrtf(3.0f);
+      const float c2_over_3 = c2 * s_inv3;
+      float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+      if (a_over_3 > 0.0f) a_over_3 = 0.0f;
+      const float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+      float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+      if (q > 0.0f) q = 0.0f;
+      const float rho = sqrtf(-a_over_3);
+      const float theta = atan2f(sqrtf(-q), half_b) * s_inv3;
+      const float ct = cosf(theta), st = sinf(theta);
+      roots[0] = c2_over_3 + 2.0f * rho * ct;
+      roots[1] = c2_over_3 - rho * (ct + s_sqrt3 * st);
+      roots[2] = c2_over_3 - rho * (ct - s_sqrt3 * st);
+      float t;
+      if (roots[0] >= roots[1]) { t = roots[0]; roots[0] = roots[1]; roots[1] = t; }
+      if (roots[1] >= roots[2]) {
+        t = roots[1]; roots[1] = roots[2]; roots[2] = t;
+        if (roots[0] >= roots[1]) { t = roots[0]; roots[0] = roots[1]; roots[1] = t; }
+      }
+      if (roots[0] <= 0.0f) pcl_roots2_f32(c2, c1, roots);
+    }
+  }
+  for (int r = 0; r < 3; ++r) m[r][r] -= roots[0];
+  float v[3][3];
+  const int pr[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+  float len[3];
+  for (int k = 0; k < 3; ++k) {
+    const float* A = m[pr[k][0]];
+    const float* B = m[pr[k][1]];
+    v[k][0] = A[1] * B[2] - A[2] * B[1];
+    v[k][1] = A[2] * B[0] - A[0] * B[2];
+    v[k][2] = A[0] * B[1] - A[1] * B[0];
+    len[k] = v[k][0] * v[k][0] + v[k][1] * v[k][1] + v[k][2] * v[k][2];
+  }
+  int best = 2;
+  if (len[0] >= len[1] && len[0] >= len[2]) best = 0;
+  else if (len[1] >= len[0] && len[1] >= len[2]) best = 1;
+  const float nrm = sqrtf(len[best]);
+  out[0] = v[best][0] / nrm;
+  out[1] = v[best][1] / nrm;
+  out[2] = v[best][2] / nrm;
+  out[3] = -1.0f * (out[0] * a[6] + out[1] * a[7] + out[2] * a[8]);
+}
+
 static int plane_ransac(const float* xyz /* C x 3 */, int C, const ilcc2o_params* P, float plane[4],
                         int* inl /* out, C */, int* n_best_out, int* iters_out) {
   rnd_ensure();
@@ -471,6 +583,7 @@ static int plane_ransac(const float* xyz /* C x 3 */, int C, const ilcc2o_params
   refined[1] = (float)ny;
   refined[2] = (float)nz;
   refined[3] = (float)(-(nx * cx + ny * cy + nz * cz));
+  if (g_variant & ILCC2O_VAR_REFIT_PCL_F32) pcl_plane_refit_f32(xyz, inl, ni, refined);
   /* re-select inliers against the refined plane */
   int nr = 0;
   for (int i = 0; i < C; ++i)
@@ -543,7 +656,10 @@ void ilcc2o_eigen3f(const float cov[9], float evals[3], float evecs[9]) {
   const float precision = 1e-5f; /* NumTraits<float>::dummy_precision() */
   while (end > 0) {
     for (int i = start; i < end; ++i)
-      if (fabsf(sub[i]) <= (fabsf(diag[i]) + fabsf(diag[i + 1])) * precision) sub[i] = 0.0f;
+      if ((g_variant & ILCC2O_VAR_EIGEN33_DEFL)
+              ? (fabsf(sub[i]) <= (fabsf(diag[i]) + fabsf(diag[i + 1])) * (2.0f * FLT_EPSILON) || fabsf(sub[i]) <= FLT_MIN)
+              : (fabsf(sub[i]) <= (fabsf(diag[i]) + fabsf(diag[i + 1])) * precision))
+        sub[i] = 0.0f;
     while (end > 0 && sub[end - 1] == 0.0f) end--;
     if (end <= 0) break;
     iter++;
@@ -632,6 +748,32 @@ void ilcc2o_eigen3f(const float cov[9], float evals[3], float evecs[9]) {
 /* a6: transformbyPCA (LidarCornersEst.cpp:330-364).  Centroid / covariance accumulate in       */
 /* double in canonical order and are narrowed to float (PCL accumulates in float, sequentially). */
 /* ------------------------------------------------------------------------------------------ */
+/* [UPSTREAM PCL 1.7 + Eigen 3.2] compute3DCentroid / computeCovarianceMatrixNormalized as PCL writes them:
+ * sequential fp32 accumulation in input order; Eigen 3.2's `vec /= n` multiplies by (1/n). */
+static void pcl_centroid_cov_f32(const float* xyz, int B, float c[3], float cov6[6]) {
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+  for (int i = 0; i < B; ++i) {
+    s0 += xyz[3 * i + 0];
+    s1 += xyz[3 * i + 1];
+    s2 += xyz[3 * i + 2];
+  }
+  const float inv = 1.0f / (float)B;
+  c[0] = s0 * inv;
+  c[1] = s1 * inv;
+  c[2] = s2 * inv;
+  float xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0;
+  for (int i = 0; i < B; ++i) {
+    const float px = xyz[3 * i + 0] - c[0], py = xyz[3 * i + 1] - c[1], pz = xyz[3 * i + 2] - c[2];
+    yy += py * py;
+    yz += py * pz;
+    zz += pz * pz;
+    xx += px * px;
+    xy += py * px;
+    xz += pz * px;
+  }
+  cov6[0] = xx * inv; cov6[1] = xy * inv; cov6[2] = xz * inv; cov6[3] = yy * inv; cov6[4] = yz * inv; cov6[5] = zz * inv;
+}
+
 static void pca_frame(const float* xyz /* B x 3 */, int B, float T[16], float evals[3]) {
   racc a[3];
   for (int q = 0; q < 3; ++q) racc_zero(&a[q]);
@@ -656,9 +798,14 @@ static void pca_frame(const float* xyz /* B x 3 */, int B, float T[16], float ev
     racc_add(&m[5], i, dz * dz);
   }
   float cov[9];
-  const float cxx = (float)(racc_total(&m[0]) / (double)B), cxy = (float)(racc_total(&m[1]) / (double)B);
-  const float cxz = (float)(racc_total(&m[2]) / (double)B), cyy = (float)(racc_total(&m[3]) / (double)B);
-  const float cyz = (float)(racc_total(&m[4]) / (double)B), czz = (float)(racc_total(&m[5]) / (double)B);
+  float cxx = (float)(racc_total(&m[0]) / (double)B), cxy = (float)(racc_total(&m[1]) / (double)B);
+  float cxz = (float)(racc_total(&m[2]) / (double)B), cyy = (float)(racc_total(&m[3]) / (double)B);
+  float cyz = (float)(racc_total(&m[4]) / (double)B), czz = (float)(racc_total(&m[5]) / (double)B);
+  if (g_variant & ILCC2O_VAR_PCA_PCL_F32) {
+    float c6[6];
+    pcl_centroid_cov_f32(xyz, B, c, c6);
+    cxx = c6[0]; cxy = c6[1]; cxz = c6[2]; cyy = c6[3]; cyz = c6[4]; czz = c6[5];
+  }
   cov[0] = cxx; cov[1] = cxy; cov[2] = cxz;
   cov[3] = cxy; cov[4] = cyy; cov[5] = cyz;
   cov[6] = cxz; cov[7] = cyz; cov[8] = czz;
@@ -769,21 +916,49 @@ int ilcc2o_gray_zone(const float* inten, int32_t n, const ilcc2o_params* P, doub
 
 /* ------------------------------------------------------------------------------------------ */
 /* a9: VirtualboardError::operator() (Optimization.h:31-107) with its autodiff Jacobian.        */
-/* x = (theta, t_y, t_z).  [UPSTREAM Ceres] AngleAxisRotatePoint about the x axis reduces to     */
-/* y' = y cos - z sin, z' = z cos + y sin; Jet division by the constant grid length multiplies   */
-/* by its reciprocal, so i = (y' + W g / 2) * (1/g).                                            */
+/* x = (theta, t_y, t_z).  [UPSTREAM Ceres rotation.h] AngleAxisRotatePoint with angle_axis =     */
+/* (theta, 0, 0): for theta^2 > DBL_EPSILON  w0 = theta * (1 / |theta|)  (+-1 or +-(1 - 2^-53)),   */
+/* y' = y cos|theta| + (-(w0 z)) sin|theta|,  z' = z cos|theta| + (w0 y) sin|theta|  (the w (w.pt)  */
+/* (1 - cos) term is an exact zero); else  y' = y - theta z,  z' = z + theta y.                   */
+/* Ceres calls the functor with T = double when only the cost is wanted (candidate evaluation):  */
+/* i = (y' + W g / 2) / g is then a true division; with T = Jet (residuals + Jacobian at an      */
+/* accepted point) Jet / Jet multiplies by the reciprocal of the divisor: i = (...) * (1 / g).   */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
   int W, H, tlw, oob;
   double g, inv_g, wg2, hg2, huber_a, huber_b;
 } vb_model;
 
-static inline double vb_point(const vb_model* M, double y, double z, int white, double c, double s,
+typedef struct {
+  double c, s; /* cos|theta|, sin|theta| (1, theta in the small-angle branch) */
+  double w0;   /* theta / |theta| as Ceres computes it (1 in the small-angle branch, where s carries the sign) */
+  double cs, ss; /* cos(theta), sin(theta): the analytic Jacobian below uses the signed pair */
+} vb_rot;
+
+static void vb_rot_init(vb_rot* R, double theta) {
+  const double theta2 = theta * theta;
+  R->cs = cos(theta);
+  R->ss = sin(theta);
+  if (theta2 > DBL_EPSILON) {
+    const double t = sqrt(theta2);
+    R->c = cos(t);
+    R->s = sin(t);
+    const double tinv = 1.0 / t;
+    R->w0 = (g_variant & ILCC2O_VAR_AXIS_UNIT) ? (theta < 0.0 ? -1.0 : 1.0) : theta * tinv;
+  } else {
+    R->c = 1.0;
+    R->s = theta;
+    R->w0 = 1.0;
+  }
+}
+
+static inline double vb_point(const vb_model* M, const vb_rot* R, int jet, double y, double z, int white,
                               double ty, double tz, double* si, double* sj) {
-  const double yy = (y * c - z * s) + ty;
-  const double zz = (z * c + y * s) + tz;
-  const double fi = (yy + M->wg2) * M->inv_g;
-  const double fj = (zz + M->hg2) * M->inv_g;
+  const double yy = (y * R->c + (-(R->w0 * z)) * R->s) + ty;
+  const double zz = (z * R->c + (R->w0 * y) * R->s) + tz;
+  const int recip = jet || (g_variant & ILCC2O_VAR_COST_RECIP);
+  const double fi = recip ? (yy + M->wg2) * M->inv_g : (yy + M->wg2) / M->g;
+  const double fj = recip ? (zz + M->hg2) * M->inv_g : (zz + M->hg2) / M->g;
   *si = 0.0;
   *sj = 0.0;
   if (fi > 0.0 && fi < (double)M->W && fj > 0.0 && fj < (double)M->H) {
@@ -808,6 +983,14 @@ static inline double vb_point(const vb_model* M, double y, double z, int white, 
       *sj = 1.0;
     }
     return ei + ej;
+  }
+  if (M->oob && !jet && (g_variant & ILCC2O_VAR_INT_ABS)) {
+    /* unqualified abs(double) resolving to ::abs(int) (glibc <stdlib.h> under libstdc++ < 6): operands truncated */
+    const int a0 = abs((int)fi), a1 = abs((int)(fi - (double)M->W));
+    const int b0 = abs((int)fj), b1 = abs((int)(fj - (double)M->H));
+    *si = 0.0;
+    *sj = 0.0;
+    return (double)(a0 < a1 ? a0 : a1) + (double)(b0 < b1 ? b0 : b1);
   }
   if (M->oob) {
     double ei, ej;
@@ -849,9 +1032,11 @@ double ilcc2o_residual(double y, double z, int white, const double x[3], int W, 
                        int topleft_white, int use_oob, double jac[3]) {
   vb_model M;
   vb_model_init(&M, W, H, g, topleft_white, use_oob, 0.1);
-  const double c = cos(x[0]), s = sin(x[0]);
+  vb_rot R;
+  vb_rot_init(&R, x[0]);
+  const double c = R.cs, s = R.ss;
   double si, sj;
-  const double r = vb_point(&M, y, z, white, c, s, x[1], x[2], &si, &sj);
+  const double r = vb_point(&M, &R, jac != NULL, y, z, white, x[1], x[2], &si, &sj);
   if (jac) {
     const double dyy = -(y * s) - (z * c);
     const double dzz = (y * c) - (z * s);
@@ -894,12 +1079,13 @@ static void trace_eval(const double x[3], int kind) {
 static double eval_cost(vb_problem* Pb, const double x[3]) {
   const vb_model* M = Pb->M;
   trace_eval(x, 0);
-  const double c = cos(x[0]), s = sin(x[0]);
+  vb_rot R;
+  vb_rot_init(&R, x[0]);
   racc a;
   racc_zero_w(&a, RW_WARP);
   for (int k = 0; k < Pb->n; ++k) {
     double si, sj;
-    const double r = vb_point(M, Pb->yz[2 * k], Pb->yz[2 * k + 1], Pb->white[k], c, s, x[1], x[2], &si, &sj);
+    const double r = vb_point(M, &R, 0, Pb->yz[2 * k], Pb->yz[2 * k + 1], Pb->white[k], x[1], x[2], &si, &sj);
     if (r != 0.0) racc_add(&a, k, huber_cost(M, r));
   }
   Pb->n_evals++;
@@ -914,14 +1100,16 @@ static double eval_cost(vb_problem* Pb, const double x[3]) {
 static void eval_jac(vb_problem* Pb, const double x[3], double* cost, double g[3], double H[6]) {
   const vb_model* M = Pb->M;
   trace_eval(x, 1);
-  const double c = cos(x[0]), s = sin(x[0]);
+  vb_rot R;
+  vb_rot_init(&R, x[0]);
+  const double c = R.cs, s = R.ss;
   racc a[10];
   for (int q = 0; q < 10; ++q) racc_zero_w(&a[q], RW_WARP);
   int j = 0;
   for (int k = 0; k < Pb->n; ++k) {
     double si, sj;
     const double y = Pb->yz[2 * k], z = Pb->yz[2 * k + 1];
-    const double r = vb_point(M, y, z, Pb->white[k], c, s, x[1], x[2], &si, &sj);
+    const double r = vb_point(M, &R, 1, y, z, Pb->white[k], x[1], x[2], &si, &sj);
     if (r == 0.0) continue;
     const double dyy = -(y * s) - (z * c);
     const double dzz = (y * c) - (z * s);
@@ -1028,6 +1216,10 @@ int ilcc2o_tr_boundary_2d(const double B[3], const double g[2], double radius, d
   if (!(fabs(n - radius) <= 1e-6 * radius)) return 0;
   x_out[0] = x[0];
   x_out[1] = x[1];
+  if (g_tr_perturb_ulps) { /* sensitivity probe: Ceres gets this point from quartic roots, not from this iteration */
+    x_out[0] = x[0] * (1.0 + (double)g_tr_perturb_ulps * DBL_EPSILON);
+    x_out[1] = x[1] * (1.0 - (double)g_tr_perturb_ulps * DBL_EPSILON);
+  }
   return 1;
 }
 
@@ -1500,11 +1692,19 @@ int ilcc2o_extract_frame(const void* points, int32_t n, int32_t point_step,
     /* a10: get_corners default key path (:374-450) */
     const int W = P->cells_x, H = P->cells_y;
     vb_model Mo;
-    for (int h = 0; h < 2; ++h) {
-      const int run = (flags & ILCC2O_FLAG_AUTO) ? 1 : (h == 0 || (flags & ILCC2O_FLAG_TOPLEFT_WHITE));
-      if (!run) continue;
+    /* hypothesis sequence: auto = (0, 1) each from zero; manual = 0, then 1 if 'd' was pressed, then (test-only
+     * variant) extra pairs of 'd' presses -- every press toggles topleftWhite and re-optimises from the current
+     * theta_t (LidarCornersEst.cpp:398-409) */
+    int seq[2 + 64], nseq = 0;
+    seq[nseq++] = 0;
+    if (flags & (ILCC2O_FLAG_AUTO | ILCC2O_FLAG_TOPLEFT_WHITE)) seq[nseq++] = 1;
+    if (!(flags & ILCC2O_FLAG_AUTO))
+      for (int e = 0; e < 2 * g_extra_d_pairs && nseq < 66; ++e) seq[nseq] = 1 - seq[nseq - 1], ++nseq;
+    double xw[3] = {0.0, 0.0, 0.0};
+    for (int qi = 0; qi < nseq; ++qi) {
+      const int h = seq[qi];
       double x[3] = {0.0, 0.0, 0.0};
-      if (h == 1 && !(flags & ILCC2O_FLAG_AUTO)) memcpy(x, D.theta_t[0], sizeof(x)); /* 'd': warm start */
+      if (qi > 0 && !(flags & ILCC2O_FLAG_AUTO)) memcpy(x, xw, sizeof(x)); /* 'd': warm start */
       int evals = 0;
       for (int phase = 0; phase < 2; ++phase) {
         vb_model_init(&Mo, W, H, P->grid_length, h, phase == 0, P->huber_delta);
@@ -1519,6 +1719,7 @@ int ilcc2o_extract_frame(const void* points, int32_t n, int32_t point_step,
       }
       D.n_evals[h] = evals;
       memcpy(D.theta_t[h], x, sizeof(x));
+      memcpy(xw, x, sizeof(x));
     }
     if (flags & ILCC2O_FLAG_AUTO)
       D.hyp_chosen = (D.cost[1] < D.cost[0]) ? 1 : 0;

@@ -159,6 +159,18 @@ void ilcc2o_project_points(const void* points, int64_t n, int32_t step, int32_t 
                            int32_t* pix_xy, uint8_t* rgbv);
 void ilcc2o_compose_extrinsic(const double r[3], const double t[3], const double T_axis[16], double T_out[16]);
 
+/* test-only restatement switches: each bit swaps ONE documented restatement choice for its alternative, so that
+ * tools/deviation_table.py can measure how far the shipped-fixture residual moves under it.
+ * mask 0 = the choices the oracle (and the CUDA kernels) ship with. */
+#define ILCC2O_VAR_COST_RECIP      1u  /* cost-only pass multiplies by 1/g like the Jet pass (Ceres: T=double divides) */
+#define ILCC2O_VAR_AXIS_UNIT       2u  /* rotation axis taken as exactly +-1 (Ceres: theta * (1/|theta|), 1 or 1-2^-53) */
+#define ILCC2O_VAR_PCA_PCL_F32     4u  /* PCL's sequential fp32 compute3DCentroid / computeCovarianceMatrixNormalized */
+#define ILCC2O_VAR_REFIT_PCL_F32   8u  /* PCL's fp32 raw-moment computeMeanAndCovarianceMatrix + closed-form eigen33 refit */
+#define ILCC2O_VAR_EIGEN33_DEFL   16u  /* Eigen 3.3 deflation test in SelfAdjointEigenSolver (3.2: dummy_precision 1e-5) */
+#define ILCC2O_VAR_INT_ABS        32u  /* T=double pass: the functor's unqualified abs() resolves to ::abs(int) (GCC 5 / glibc) */
+void ilcc2o_set_variant(uint32_t mask, int extra_d_pairs, int tr_perturb_ulps);
+uint32_t ilcc2o_get_variant(void);
+
 /* test-only: record the evaluation points of the solves run by the calling thread (4 doubles each: x[0..2], kind) */
 void ilcc2o_trace(double* buf, int cap);
 void ilcc2o_tr2_stats(long long* calls, long long* iters, int reset);

@@ -92,6 +92,8 @@ def lib() -> C.CDLL:
                                            C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32,
                                            C.POINTER(Params), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ilcc2o_max_threads.restype = C.c_int
+        L.ilcc2o_set_variant.argtypes = [C.c_uint32, C.c_int, C.c_int]
+        L.ilcc2o_get_variant.restype = C.c_uint32
         L.ilcc2o_pcl_rnd.restype = C.c_uint32
         L.ilcc2o_pcl_rnd.argtypes = [C.c_int]
         L.ilcc2o_eigen3f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]

@@ -161,3 +161,39 @@ def test_solver_decreases_cost_and_warm_start_is_a_fixed_point(oracle):
     _, _, cost0, _, _ = oracle.solve(yz, white, [0, 0, 0], W, H, g, False, False, max_iter=0)
     assert abs(x2[0] - th) < 1e-2 and abs(x2[1] - ty) < 6e-3 and abs(x2[2] - tz) < 6e-3 and cost2 < 0.2 * cost0
     assert it <= 50 and it2 <= 50
+
+
+def test_reciprocal_correction_equals_true_division():
+    """The kernels' cost-only pass takes x / g (Optimization.h:45-46 with T = double) as q = x * (1/g); r = fma(-q, g, x);
+    q + r * (1/g) -- exact IEEE division for the correctly rounded reciprocal.  Checked here with exact fma emulation
+    (math.fma needs 3.13; fractions are exact) on values around the cell borders the floor() of the residual sees."""
+    from fractions import Fraction
+    rng = np.random.default_rng(7)
+    g = 0.15
+    inv_g = 1.0 / g
+
+    def fma(a, b, c):  # correctly rounded a*b+c
+        return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+    xs = np.concatenate([rng.uniform(-0.2, 1.4, 4000), np.arange(0, 9) * 0.15, np.nextafter(np.arange(0, 9) * 0.15, 10),
+                         np.nextafter(np.arange(0, 9) * 0.15, -10), rng.uniform(-1e-12, 1e-12, 200)])
+    for x in xs:
+        x = float(x)
+        q = x * inv_g
+        r = fma(-q, g, x)
+        assert fma(r, inv_g, q) == x / g, x
+
+
+def test_restatement_switches_move_the_fixture_result_by_microns(oracle, bag_clouds, fixtures):
+    """profiles/deviation_table_r2.md in one assertion: the arithmetic choices of the restatement (reciprocal vs true
+    division, rotation axis, PCL's sequential fp32 moments, refit solver) move the corners of bag 1 by < 5e-6 m."""
+    fx = np.asarray(fixtures["lidar_corners"]["1"])
+    L = oracle.lib()
+    base = oracle.extract_frame(bag_clouds[1], fx.mean(0), flags=1)[1]
+    try:
+        for mask in (1, 2, 4, 8):
+            L.ilcc2o_set_variant(mask, 0, 0)
+            c = oracle.extract_frame(bag_clouds[1], fx.mean(0), flags=1)[1]
+            assert np.abs(c - base).max() < 5e-6, mask
+    finally:
+        L.ilcc2o_set_variant(0, 0, 0)
