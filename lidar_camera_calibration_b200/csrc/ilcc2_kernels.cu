@@ -1302,7 +1302,7 @@ void launch_pca_gray(const Workspace& w, const DevParams& p, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 struct VbModel {
   int tlw;
-  double Wd, Hd, inv_g, wg2, hg2, ha, hb, two_ha;
+  double Wd, Hd, g, inv_g, wg2, hg2, ha, hb, two_ha;
   float ymax_zmax;  // max|y'| + max|z'| over the frame's points (for the fp32 error bound)
 };
 
@@ -1321,14 +1321,36 @@ struct FitPts {
   int team_cap;  // points per chunk
 };
 
+// Lattice coordinates of a point, (y' + W g / 2) / g (Optimization.h:45-46), the way Ceres evaluates them:
+//   rotation  AngleAxisRotatePoint((theta, 0, 0)): y' = y cos - (w0 z) sin, z' = z cos + (w0 y) sin with
+//             w0 = |theta| * (1 / |theta|) (1 or 1 - 2^-53; 1 in the small-angle branch) -- `w0` below;
+//   JET true  (residuals + Jacobian at an accepted point, T = Jet): Jet / Jet multiplies by the reciprocal of g;
+//   JET false (cost of a candidate, T = double): a true division, taken here as q = x (1/g), q + fma(-q, g, x) (1/g),
+//             which is the correctly rounded quotient for the correctly rounded reciprocal (Markstein), 2 FMAs instead of
+//             the ~50-instruction IEEE division sequence.
+template <bool JET>
+__device__ __forceinline__ void vb_lattice(const VbModel& M, double y, double z, double c, double s, double w0, double ty,
+                                           double tz, double& fi, double& fj) {
+  const double yy = (y * c - (w0 * z) * s) + ty;
+  const double zz = (z * c + (w0 * y) * s) + tz;
+  const double xi = yy + M.wg2, xj = zz + M.hg2;
+  const double qi = xi * M.inv_g, qj = xj * M.inv_g;
+  if (JET) {
+    fi = qi;
+    fj = qj;
+  } else {
+    fi = fma(fma(-qi, M.g, xi), M.inv_g, qi);
+    fj = fma(fma(-qj, M.g, xj), M.inv_g, qj);
+  }
+}
+
 // exact residual of one point (Optimization.h:31-107) with the signs of its autodiff Jacobian, branch-free
 // except for the (warp-uniform) useOutofBoard switch. wx = laser_white ^ topleftWhite.
+template <bool JET>
 __device__ __forceinline__ double vb_eval(const VbModel& M, bool oob, double y, double z, unsigned wx, double c,
-                                          double s, double ty, double tz, double& si, double& sj) {
-  const double yy = (y * c - z * s) + ty;
-  const double zz = (z * c + y * s) + tz;
-  const double fi = (yy + M.wg2) * M.inv_g;
-  const double fj = (zz + M.hg2) * M.inv_g;
+                                          double s, double w0, double ty, double tz, double& si, double& sj) {
+  double fi, fj;
+  vb_lattice<JET>(M, y, z, c, s, w0, ty, tz, fi, fj);
   const bool in = fi > 0.0 && fi < M.Wd && fj > 0.0 && fj < M.Hd;
   // floor for 0 <= f < 2^51: (f + 2^52) - 2^52 rounds to the nearest integer, step back if it went up
   const double kMagic = 4503599627370496.0;
@@ -1365,12 +1387,11 @@ __device__ __forceinline__ double vb_eval(const VbModel& M, bool oob, double y, 
 
 // residual (and Jacobian signs) of a point that is certainly outside the board: the useOutofBoard branch,
 // Optimization.h:86-101 -- same expressions as the corresponding part of vb_eval.
-__device__ __forceinline__ double vb_eval_out(const VbModel& M, double y, double z, double c, double s, double ty,
-                                              double tz, double& si, double& sj) {
-  const double yy = (y * c - z * s) + ty;
-  const double zz = (z * c + y * s) + tz;
-  const double fi = (yy + M.wg2) * M.inv_g;
-  const double fj = (zz + M.hg2) * M.inv_g;
+template <bool JET>
+__device__ __forceinline__ double vb_eval_out(const VbModel& M, double y, double z, double c, double s, double w0,
+                                              double ty, double tz, double& si, double& sj) {
+  double fi, fj;
+  vb_lattice<JET>(M, y, z, c, s, w0, ty, tz, fi, fj);
   const double fiw = fi - M.Wd, fjh = fj - M.Hd;
   const double a0 = fabs(fi), a1 = fabs(fiw);
   const double b0 = fabs(fj), b1 = fabs(fjh);
@@ -1582,16 +1603,11 @@ __device__ __forceinline__ void accumulate_point(const VbModel& M, bool want_jac
 }
 
 // exact fp64 evaluation of the listed points (all lanes busy; uniform trip counts because of __any_sync).
-// want_jac = false: a[0] += Huber cost.  want_jac = true: a[0..2] += J^T r, a[3..8] += J^T J.
-template <typename IdxT>
+// JAC = false: a[0] += Huber cost (Ceres' T = double pass).  JAC = true: a[0..2] += J^T r, a[3..8] += J^T J (Jet pass).
+template <typename IdxT, bool JAC>
 __device__ __forceinline__ void list_pass(const float2* __restrict__ yz, const uint32_t* __restrict__ wbits,
-                                          const IdxT* list, int list_cap, const VbModel& M, bool oob, bool want_jac,
-                                          double c, double s, double ty, double tz, int lane, int n1, int n2,
-                                          double (&a)[9]) {
-#ifndef LIST_U
-#define LIST_U 1
-#endif
-#if LIST_U == 1
+                                          const IdxT* list, int list_cap, const VbModel& M, bool oob, double c, double s,
+                                          double w0, double ty, double tz, int lane, int n1, int n2, double (&a)[9]) {
   // L1: colour mismatch or not certain -> full residual.  Software pipeline: index, point and colour bit of the next
   // iteration are fetched (shared-memory list -> L1 gather, a dependent chain) while this one is evaluated.
   int kn = lane < n1 ? (int)list[lane] : 0;
@@ -1608,29 +1624,10 @@ __device__ __forceinline__ void list_pass(const float2* __restrict__ yz, const u
     wn = wbits[kn >> 5];
     const double y = (double)q.x, z = (double)q.y;
     double si, sj;
-    double r = vb_eval(M, oob, y, z, wx, c, s, ty, tz, si, sj);
+    double r = vb_eval<JAC>(M, oob, y, z, wx, c, s, w0, ty, tz, si, sj);
     if (!act) r = 0.0;
-    accumulate_point(M, want_jac, y, z, c, s, r, si, sj, a);
+    accumulate_point(M, JAC, y, z, c, s, r, si, sj, a);
   }
-#else
-  for (int e0 = 0; e0 < n1; e0 += 32 * LIST_U) {  // L1: colour mismatch or not certain -> full residual
-    double y[LIST_U], z[LIST_U], r[LIST_U], si[LIST_U], sj[LIST_U];
-#pragma unroll
-    for (int u = 0; u < LIST_U; ++u) {  // LIST_U independent points per lane: the fp64 chain is latency-bound
-      const int e = e0 + 32 * u + lane;
-      const bool act = e < n1;
-      const int k = act ? (int)list[e] : 0;
-      const float2 q = __ldg(yz + k);
-      const unsigned wx = ((wbits[k >> 5] >> (k & 31)) & 1u) ^ (unsigned)M.tlw;
-      y[u] = (double)q.x;
-      z[u] = (double)q.y;
-      r[u] = vb_eval(M, oob, y[u], z[u], wx, c, s, ty, tz, si[u], sj[u]);
-      if (!act) r[u] = 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < LIST_U; ++u) accumulate_point(M, want_jac, y[u], z[u], c, s, r[u], si[u], sj[u], a);
-  }
-#endif
   if (oob) {
     for (int e0 = 0; e0 < n2; e0 += 32) {  // L2: certainly outside the board -> distance to the nearest edges
       const int e = e0 + lane;
@@ -1639,9 +1636,9 @@ __device__ __forceinline__ void list_pass(const float2* __restrict__ yz, const u
       const float2 q = yz[k];
       const double y = (double)q.x, z = (double)q.y;
       double si, sj;
-      double r = vb_eval_out(M, y, z, c, s, ty, tz, si, sj);
+      double r = vb_eval_out<JAC>(M, y, z, c, s, w0, ty, tz, si, sj);
       if (!act) r = 0.0;
-      accumulate_point(M, want_jac, y, z, c, s, r, si, sj, a);
+      accumulate_point(M, JAC, y, z, c, s, r, si, sj, a);
     }
   }
 }
@@ -1989,6 +1986,12 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
     // ---- cost at the candidate ----
     double sn, cs;
     sincos_once(cand[0], &sn, &cs);
+    // AngleAxisRotatePoint's unit axis: theta * (1 / |theta|), which is 1 or 1 - 2^-53 (small-angle branch: 1)
+    double w0 = 1.0;
+    {
+      const double at = fabs(cand[0]);
+      if (at * at > DBL_EPSILON) w0 = at * ddiv(1.0, at);
+    }
     double a[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) a[q] = 0.0;
@@ -2004,7 +2007,7 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
 #ifdef FIT_TIMING
       t_cls += clock64() - tc0;
 #endif
-      list_pass<IdxT>(yz, wbits, list, list_cap, M, oob, false, cs, sn, cand[1], cand[2], lane, n1, n2, a);
+      list_pass<IdxT, false>(yz, wbits, list, list_cap, M, oob, cs, sn, w0, cand[1], cand[2], lane, n1, n2, a);
       if (k0 + team_cap < n) __syncwarp();
     }
     double cc1[1] = {warp_butterfly(a[0])};
@@ -2033,14 +2036,14 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
 #pragma unroll
       for (int q = 0; q < 9; ++q) a[q] = 0.0;
       if (n <= team_cap) {
-        list_pass<IdxT>(yz, wbits, list, list_cap, M, oob, true, cs, sn, xc[1], xc[2], lane, n1, n2, a);
+        list_pass<IdxT, true>(yz, wbits, list, list_cap, M, oob, cs, sn, w0, xc[1], xc[2], lane, n1, n2, a);
       } else {
         for (int k0 = 0; k0 < n; k0 += team_cap) {
           __syncwarp();
           const int k1 = min(k0 + team_cap, n);
           classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, xc[1], xc[2], lane, k0 + wt * (32 * CLS_UNROLL), k1,
                               T * 32 * CLS_UNROLL, n1, n2);
-          list_pass<IdxT>(yz, wbits, list, list_cap, M, oob, true, cs, sn, xc[1], xc[2], lane, n1, n2, a);
+          list_pass<IdxT, true>(yz, wbits, list, list_cap, M, oob, cs, sn, w0, xc[1], xc[2], lane, n1, n2, a);
         }
       }
 #pragma unroll
@@ -2300,6 +2303,7 @@ __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) boa
   VbModel M;
   M.Wd = (double)p.W;
   M.Hd = (double)p.H;
+  M.g = p.g;
   M.inv_g = p.inv_g;
   M.wg2 = p.wg2;
   M.hg2 = p.hg2;

@@ -340,3 +340,43 @@ def project_points(points: np.ndarray, T_lidar2cam, camera, width, height, dista
                                 distance_valid, inten_low, inten_high, None if img is None else img.ctypes.data,
                                 pix.ctypes.data, rgbv.ctypes.data)
     return pix, rgbv
+
+
+# ---- parity of a whole batch against this oracle (bench.py's cpu_baseline leg and tests/) ----
+def parity_report(points: np.ndarray, clicks: np.ndarray, status_gpu: np.ndarray, corners_gpu: np.ndarray,
+                  diags_gpu=None, flags: int = FLAG_AUTO, params: Params | None = None, threads: int = 1,
+                  tol_m: float = 1e-3) -> dict:
+    """Runs the oracle on every frame of the batch and compares: per-frame status, corner distance (same lattice
+    order, so index for index), and -- when the product's ilcc2_diag records are given -- solver iteration counts /
+    termination codes / chosen hypothesis.  Returns the `parity` block of bench.py's JSON line."""
+    t0 = __import__("time").time()
+    st, corners, diags = extract_batch(points, clicks, flags=flags, params=params, threads=threads, want_diag=True)
+    dt = __import__("time").time() - t0
+    status_gpu = np.asarray(status_gpu)
+    corners_gpu = np.asarray(corners_gpu, np.float64)
+    F = int(st.size)
+    same_status = st == status_gpu
+    ok = (st == 0) & (status_gpu == 0)
+    err = np.zeros(F)
+    if ok.any():
+        err[ok] = np.linalg.norm(corners_gpu[ok] - corners[ok].astype(np.float64), axis=2).max(axis=1)
+    out = {"frames": F, "frames_ok": int(ok.sum()), "status_equal": bool(same_status.all()),
+           "status_mismatch_frames": np.flatnonzero(~same_status)[:16].tolist(),
+           "max_corner_err_m": float(err.max()) if F else 0.0,
+           "frac_within_1e-3": float((err[ok] <= tol_m).mean()) if ok.any() else None,
+           "frames_beyond_tol": np.flatnonzero(err > tol_m)[:16].tolist(),
+           "p99_corner_err_m": float(np.percentile(err[ok], 99)) if ok.any() else None,
+           "oracle_s": dt, "oracle_threads": threads}
+    if diags_gpu is not None:
+        it_eq = hyp_eq = term_eq = 0
+        worst_theta = 0.0
+        for f in np.flatnonzero(ok):
+            a, b = diags[f], diags_gpu[f]
+            it_eq += int(np.array_equal(a["iters"], b["iters"]))
+            term_eq += int(np.array_equal(a["term"], b["term"]))
+            hyp_eq += int(a["hyp_chosen"] == b["hyp_chosen"])
+            worst_theta = max(worst_theta, float(np.abs(np.asarray(a["theta_t"]) - np.asarray(b["theta_t"])).max()))
+        n = max(int(ok.sum()), 1)
+        out.update({"iters_equal_frac": it_eq / n, "term_equal_frac": term_eq / n, "hyp_equal_frac": hyp_eq / n,
+                    "max_theta_t_diff": worst_theta})
+    return out

@@ -344,6 +344,42 @@ def test_batch_properties_at_bench_size(api):
     assert np.median(acc) < 5e-3 and np.mean(acc < 2e-2) > 0.6
 
 
+def test_bench_batch_parity_with_the_oracle(api, oracle):
+    """The batch bench.py's headline number is measured on -- 1024 synthetic VLP-16 frames, seeds 0..1023, colour phase
+    auto -- compared with the oracle frame for frame ("report the fraction within 1e-3 m and the
+    max"): identical statuses, every corner of every OK frame within the north-star tolerance of 1e-3 m, identical
+    chosen hypothesis, and solver iteration counts / termination codes equal on all frames (the candidate lists group
+    the sums differently and CUDA's sincos is not glibc's, so theta and t agree to rounding only)."""
+    import os
+    from lidar_camera_calibration_b200 import synth
+    F = 1024
+    pts, clicks = synth.make_batch(F, start=0)
+    ex = api.CornerExtractor(F, synth.VLP16.n_points)
+    st, corners, diags = ex.extract(pts, clicks, flags=api.FLAG_AUTO, want_diag=True)
+    rep = oracle.parity_report(pts, clicks, st, corners, diags, threads=max(1, len(os.sched_getaffinity(0))))
+    print("parity (bench batch):", rep)
+    assert rep["status_equal"], rep
+    assert rep["frames_ok"] >= F - 16
+    assert rep["max_corner_err_m"] <= TOL_CORNER_M and rep["frac_within_1e-3"] == 1.0, rep
+    assert rep["hyp_equal_frac"] == 1.0 and rep["iters_equal_frac"] >= 0.995 and rep["term_equal_frac"] >= 0.995, rep
+
+
+def test_hdl64_batch_parity_with_the_oracle(api, oracle):
+    """32 HDL-64-like frames (64 x 2048 points, 9x7 board; BASELINE.json configs[3]) against the oracle."""
+    import os
+    from lidar_camera_calibration_b200 import synth
+    F = 32
+    pts, clicks = synth.make_batch(F, scene=synth.SCENE_HDL64)
+    ex = api.CornerExtractor(F, synth.HDL64.n_points, params=api.default_params(cells_x=8, cells_y=10))
+    st, corners, diags = ex.extract(pts, clicks, flags=api.FLAG_AUTO, want_diag=True)
+    rep = oracle.parity_report(pts, clicks, st, corners, diags, params=oracle.default_params(cells_x=8, cells_y=10),
+                               threads=max(1, len(os.sched_getaffinity(0))))
+    print("parity (HDL-64-like):", rep)
+    assert rep["status_equal"] and rep["frames_ok"] >= F - 2, rep
+    assert rep["max_corner_err_m"] <= TOL_CORNER_M and rep["frac_within_1e-3"] == 1.0, rep
+    assert rep["hyp_equal_frac"] == 1.0, rep
+
+
 def test_sparse_roi_overflows_the_shared_memory_cell_table(api, oracle):
     """K2 keeps 4096 hash slots in shared memory; a ROI whose points occupy more than 3072 cells (a sparse cloud: most
     points alone in their cell) is handed over to the global-memory tables.  Clusters must not depend on the path."""
