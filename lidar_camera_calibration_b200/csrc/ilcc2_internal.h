@@ -56,6 +56,10 @@ constexpr int kFitBitsCap = 8192;      // K5: colour bits kept in shared memory;
 constexpr int kFitBigFrame = 65536;
 constexpr int kFitTeamCapBig = 16384;
 constexpr int kFitBitsCapBig = 32768;
+#ifndef FIT_BATCH
+#define FIT_BATCH 8
+#endif
+constexpr int kFitBatch = FIT_BATCH;   // K5: candidates (radius halvings) prepared per trust-region model, one per lane
 constexpr int kRndTable = 8192;       // PCL RANSAC draw table length
 
 constexpr int kMaxGatherTargets = 8;   // ranks of one NVSwitch domain (or 1: a multicast mapping that reaches all of them)

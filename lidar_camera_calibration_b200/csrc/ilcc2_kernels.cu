@@ -1669,6 +1669,9 @@ struct ScalarWs {
   // inside the classification and list loops
   double xc[3], cand[3], g[3], H[6], scale[3], xbest[3];
   double x_cost, xnorm, best_cost, model_change, gmax;
+  // candidate batch (solve_tr): entry k = candidate for radius 2^-k: cand[3], model decrease (<= 0: invalid step),
+  // |step|, sin / cos of the candidate angle, unit-axis factor
+  double batch[kFitBatch][8];
 };
 
 __device__ __forceinline__ double norm3(const double v[3]) { return dsqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
@@ -1767,64 +1770,52 @@ __device__ __noinline__ bool tr_boundary_2d(const double B[3], const double g[2]
   return true;
 }
 
-__device__ void dogleg_traditional(Dogleg& S, double step[3]) {
+// Trust-region step for radius `radius` from the model held in S (read-only here, so that different lanes can ask for
+// different radii at once): traditional dogleg.  Returns |step| in the scaled space.
+__device__ double dogleg_traditional(const Dogleg& S, double radius, double step[3]) {
   const double gnorm = norm3(S.grad), gnn = S.gnn;
-  if (gnn <= S.radius) {
+  if (gnn <= radius) {
     for (int i = 0; i < 3; ++i) step[i] = S.gn[i] * S.inv_diag[i];
-    S.step_norm = gnn;
-    return;
+    return gnn;
   }
-  if (gnorm * S.alpha >= S.radius) {
-    {
-      const double sc = -ddiv(S.radius, gnorm);
-      for (int i = 0; i < 3; ++i) step[i] = (sc * S.grad[i]) * S.inv_diag[i];
-    }
-    S.step_norm = S.radius;
-    return;
+  if (gnorm * S.alpha >= radius) {
+    const double sc = -ddiv(radius, gnorm);
+    for (int i = 0; i < 3; ++i) step[i] = (sc * S.grad[i]) * S.inv_diag[i];
+    return radius;
   }
   const double b_dot_a = -S.alpha * (S.grad[0] * S.gn[0] + S.grad[1] * S.gn[1] + S.grad[2] * S.gn[2]);
   const double a2 = (S.alpha * gnorm) * (S.alpha * gnorm);
   const double bma2 = a2 - 2.0 * b_dot_a + gnn * gnn;
   const double c = b_dot_a - a2;
-  const double dd = dsqrt(c * c + bma2 * (S.radius * S.radius - a2));
-  const double beta = (c <= 0.0) ? ddiv(dd - c, bma2) : ddiv(S.radius * S.radius - a2, dd + c);
+  const double dd = dsqrt(c * c + bma2 * (radius * radius - a2));
+  const double beta = (c <= 0.0) ? ddiv(dd - c, bma2) : ddiv(radius * radius - a2, dd + c);
   double dl[3];
   for (int i = 0; i < 3; ++i) dl[i] = (-S.alpha * (1.0 - beta)) * S.grad[i] + beta * S.gn[i];
-  S.step_norm = norm3(dl);
+  const double n = norm3(dl);
   for (int i = 0; i < 3; ++i) step[i] = dl[i] * S.inv_diag[i];
+  return n;
 }
 
-__device__ void dogleg_subspace_step(Dogleg& S, double step[3]) {
-  const double gnn = S.gnn;
-  if (gnn <= S.radius) {
+// Subspace dogleg step (Ceres DoglegStrategy::ComputeSubspaceDoglegStep) for radius `radius`; returns |step| (scaled).
+__device__ __noinline__ double dogleg_step_for_radius(const Dogleg& S, double radius, double step[3]) {
+  if (S.gnn <= radius) {
     for (int i = 0; i < 3; ++i) step[i] = S.gn[i] * S.inv_diag[i];
-    S.step_norm = gnn;
-    return;
+    return S.gnn;
   }
   if (S.sub1d) {
-    const double gnorm = norm3(S.grad);
-    {
-      const double sc = -ddiv(S.radius, gnorm);
-      for (int i = 0; i < 3; ++i) step[i] = (sc * S.grad[i]) * S.inv_diag[i];
-    }
-    S.step_norm = S.radius;
-    return;
+    const double sc = -ddiv(radius, norm3(S.grad));
+    for (int i = 0; i < 3; ++i) step[i] = (sc * S.grad[i]) * S.inv_diag[i];
+    return radius;
   }
   double m2[2];
-  if (!tr_boundary_2d(S.sub_B, S.sub_g, S.tb_l1, S.tb_l2, S.tb_gn, S.radius, m2)) {
-    dogleg_traditional(S, step);
-    return;
-  }
+  if (!tr_boundary_2d(S.sub_B, S.sub_g, S.tb_l1, S.tb_l2, S.tb_gn, radius, m2)) return dogleg_traditional(S, radius, step);
   for (int i = 0; i < 3; ++i) step[i] = (S.U[i][0] * m2[0] + S.U[i][1] * m2[1]) * S.inv_diag[i];
-  S.step_norm = S.radius;
+  return radius;
 }
 
-__device__ __noinline__ bool dogleg_compute_step(Dogleg& S, const double Hs[6], const double gs[3], double step[3]) {
-  if (S.reuse) {
-    dogleg_subspace_step(S, step);
-    return true;
-  }
-  S.reuse = 1;
+// The part of DoglegStrategy::ComputeStep that does not depend on the radius: scaling diagonal, gradient, Cauchy step
+// length, mu-regularised Gauss-Newton step, 2-D subspace model.  False = linear solver failure (an invalid step).
+__device__ __noinline__ bool dogleg_build_model(Dogleg& S, const double Hs[6], const double gs[3]) {
   const double hd[3] = {Hs[0], Hs[3], Hs[5]};
   for (int i = 0; i < 3; ++i) {
     double v = hd[i];
@@ -1888,15 +1879,15 @@ __device__ __noinline__ bool dogleg_compute_step(Dogleg& S, const double Hs[6], 
     S.sub_B[0] = quad3(Hs, w0, w0);
     S.sub_B[1] = quad3(Hs, w0, w1);
     S.sub_B[2] = quad3(Hs, w1, w1);
-    const double tr = S.sub_B[0] + S.sub_B[2], hd = 0.5 * (S.sub_B[0] - S.sub_B[2]);
-    const double disc = dsqrt(hd * hd + S.sub_B[1] * S.sub_B[1]);
+    const double tr = S.sub_B[0] + S.sub_B[2], hd2 = 0.5 * (S.sub_B[0] - S.sub_B[2]);
+    const double disc = dsqrt(hd2 * hd2 + S.sub_B[1] * S.sub_B[1]);
     S.tb_l1 = 0.5 * tr - disc;
     S.tb_l2 = 0.5 * tr + disc;
     S.tb_gn = dsqrt(S.sub_g[0] * S.sub_g[0] + S.sub_g[1] * S.sub_g[1]);
   }
-  dogleg_subspace_step(S, step);
   return true;
 }
+
 
 enum { TERM_MAX_ITER = 0, TERM_GRADIENT = 1, TERM_PARAMETER = 2, TERM_FUNCTION = 3, TERM_MIN_RADIUS = 4, TERM_INVALID = 5 };
 
@@ -1927,10 +1918,19 @@ __device__ __forceinline__ void team_sum(double (&v)[NQ], double* slots /* [2][T
 // One ceres::Solve (TrustRegionMinimizer, Ceres 1.13/1.14 defaults) on one warp.  Written as a single loop
 // whose head evaluates the cost at the current candidate (the first candidate is the start point and is always
 // "accepted"), so that the classification / evaluation code exists exactly once in the kernel image.
+//
+// Candidate batches.  Between two accepted steps the model (Gauss-Newton step, 2-D subspace model) is fixed and every
+// rejection just halves the radius, so the candidates of a whole run of rejections are known in advance: the step for
+// radius r 2^-k, k = 0, 1, ...  The solver's per-candidate scalar work (the secular-equation Newton of the boundary
+// problem, the model decrease, sincos of the candidate angle) is therefore done ONCE per model, with lane k of the warp
+// working on radius r 2^-k -- all lanes were executing this code redundantly anyway -- and parked in shared memory; a
+// rejected iteration then costs one evaluation pass plus a table look-up instead of one pass plus ~2000 cycles of
+// dependent fp64 arithmetic (3.3 candidates are evaluated per accepted step on the bench batch).  Every candidate is
+// bit-identical to what the sequential formulation computes (same functions of the same radius).
 // Rejected Gauss-Newton steps that would be recomputed identically (radius still above |GN|) are fast-forwarded:
 // iteration counter and radius advance exactly as if the same candidate had been evaluated and rejected again.
 // Inlined into its single call site (the phase loop of board_fit_kernel): the model constants then come straight
-// from the kernel parameters and nothing is spilled around the call (ncu/ptxas: 216 B -> 0 B of spills, -8 % time).
+// from the kernel parameters and nothing is spilled around the call.
 template <typename IdxT, int T>
 __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* Mp, int oob_i, int max_iter, int lane,
                                      double* x, double* final_cost, int* iters_out, int* n_evals_io, double* slots,
@@ -1975,7 +1975,16 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
   S.tb_l1 = S.tb_l2 = S.tb_gn = 0.0;
   S.inv_diag[0] = S.inv_diag[1] = S.inv_diag[2] = 1.0;
   int iter = 0, invalid = 0, term = TERM_MAX_ITER, n_evals = 0;
+  int bi = 0, nb = 0;  // cursor into / entries of the candidate batch (entry k: radius at build time x 2^-k)
   bool succ = true, first = true;
+  // rotation of the candidate: sin, cos and AngleAxisRotatePoint's unit axis theta * (1 / |theta|), which is 1 or
+  // 1 - 2^-53 (small-angle branch: 1)
+  double sn, cs, w0 = 1.0;
+  sincos_once(cand[0], &sn, &cs);
+  {
+    const double at = fabs(cand[0]);
+    if (at * at > DBL_EPSILON) w0 = at * ddiv(1.0, at);
+  }
 #ifdef FIT_TIMING
   long long t_eval = 0, t_scalar = 0, t_cls = 0, t_jac = 0, t0 = clock64();
 #endif
@@ -1984,14 +1993,6 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
     { const long long t1 = clock64(); t_scalar += t1 - t0; t0 = t1; }
 #endif
     // ---- cost at the candidate ----
-    double sn, cs;
-    sincos_once(cand[0], &sn, &cs);
-    // AngleAxisRotatePoint's unit axis: theta * (1 / |theta|), which is 1 or 1 - 2^-53 (small-angle branch: 1)
-    double w0 = 1.0;
-    {
-      const double at = fabs(cand[0]);
-      if (at * at > DBL_EPSILON) w0 = at * ddiv(1.0, at);
-    }
     double a[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) a[q] = 0.0;
@@ -2056,6 +2057,7 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
       for (int q = 0; q < 6; ++q) H[q] = a[3 + q];
       gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
       succ = true;
+      nb = 0;  // new model: the parked candidates are stale
 #ifdef FIT_TIMING
       { const long long t1 = clock64(); t_jac += t1 - t0; t0 = t1; }
 #endif
@@ -2080,48 +2082,92 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
       const bool was_gn = gnn <= S.radius;
       S.radius *= 0.5;
       S.reuse = 1;
+      ++bi;
       if (was_gn) {
         // the identical Gauss-Newton candidate would be evaluated and rejected again
         while (iter < max_iter && gnn <= S.radius && S.radius > 1e-32) {
           iter++;
           S.radius *= 0.5;
+          ++bi;
         }
       }
     }
     first = false;
     // ---- next trust-region step (loops over invalid steps) ----
     bool stop = false;
-    double* step = ws.step;
-    step[0] = step[1] = step[2] = 0.0;
     for (;;) {
       if (iter >= max_iter) { term = TERM_MAX_ITER; stop = true; break; }
       if (succ && gmax <= 1e-10) { term = TERM_GRADIENT; stop = true; break; }
       if (S.radius <= 1e-32) { term = TERM_MIN_RADIUS; stop = true; break; }
       iter++;
-      double* Hs = ws.Hs;
-      double* gs = ws.gs;
-      Hs[0] = H[0] * scale[0] * scale[0];
-      Hs[1] = H[1] * scale[0] * scale[1];
-      Hs[2] = H[2] * scale[0] * scale[2];
-      Hs[3] = H[3] * scale[1] * scale[1];
-      Hs[4] = H[4] * scale[1] * scale[2];
-      Hs[5] = H[5] * scale[2] * scale[2];
-      for (int i = 0; i < 3; ++i) gs[i] = g[i] * scale[i];
-      const bool ok = dogleg_compute_step(S, Hs, gs, step);
-      bool valid = false;
-      if (ok) {
-        model_change = -((step[0] * gs[0] + step[1] * gs[1] + step[2] * gs[2]) + 0.5 * quad3(Hs, step, step));
-        valid = model_change > 0.0;
+      if (bi >= nb) {
+        // (re)build the batch from the current radius: lane k takes radius 2^-k
+        double* Hs = ws.Hs;
+        double* gs = ws.gs;
+        bool ok = true;
+        if (!S.reuse) {
+          Hs[0] = H[0] * scale[0] * scale[0];
+          Hs[1] = H[1] * scale[0] * scale[1];
+          Hs[2] = H[2] * scale[0] * scale[2];
+          Hs[3] = H[3] * scale[1] * scale[1];
+          Hs[4] = H[4] * scale[1] * scale[2];
+          Hs[5] = H[5] * scale[2] * scale[2];
+          for (int i = 0; i < 3; ++i) gs[i] = g[i] * scale[i];
+          S.reuse = 1;
+          ok = dogleg_build_model(S, Hs, gs);
+        }
+        __syncwarp();
+        const int kk = lane < kFitBatch ? lane : kFitBatch - 1;
+        const double rk = S.radius * __hiloint2double((1023 - kk) << 20, 0);  // radius 2^-k, exact
+        double st[3] = {0.0, 0.0, 0.0};
+        double stepn = 0.0, mc = -1.0;
+        if (ok) {
+          stepn = dogleg_step_for_radius(S, rk, st);
+          mc = -((st[0] * gs[0] + st[1] * gs[1] + st[2] * gs[2]) + 0.5 * quad3(Hs, st, st));
+        }
+        const double c0 = xc[0] + st[0] * scale[0], c1 = xc[1] + st[1] * scale[1], c2 = xc[2] + st[2] * scale[2];
+        double bsn, bcs, bw0 = 1.0;
+        sincos_once(c0, &bsn, &bcs);
+        {
+          const double at = fabs(c0);
+          if (at * at > DBL_EPSILON) bw0 = at * ddiv(1.0, at);
+        }
+        if (lane < kFitBatch) {
+          double* e = ws.batch[lane];
+          e[0] = c0;
+          e[1] = c1;
+          e[2] = c2;
+          e[3] = mc;
+          e[4] = stepn;
+          e[5] = bsn;
+          e[6] = bcs;
+          e[7] = bw0;
+        }
+        __syncwarp();
+        nb = kFitBatch;
+        bi = 0;
       }
-      if (valid) break;
+      const double* e = ws.batch[bi];
+      const double mc = e[3];
+      if (mc > 0.0) {
+        cand[0] = e[0];
+        cand[1] = e[1];
+        cand[2] = e[2];
+        model_change = mc;
+        S.step_norm = e[4];
+        sn = e[5];
+        cs = e[6];
+        w0 = e[7];
+        break;
+      }
       if (++invalid >= 5) { term = TERM_INVALID; stop = true; break; }
       S.mu *= 10.0;
       S.reuse = 0;
+      nb = 0;
       succ = false;
     }
     if (stop) break;
     invalid = 0;
-    for (int i = 0; i < 3; ++i) cand[i] = xc[i] + step[i] * scale[i];
   }
   for (int i = 0; i < 3; ++i) x[i] = xbest[i];
   *final_cost = best_cost;
@@ -2141,6 +2187,7 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
 #endif
   return term;
 }
+
 
 __device__ __forceinline__ void rigid_inverse(const float T[16], float O[16]) {
   for (int r = 0; r < 3; ++r)
