@@ -67,6 +67,7 @@ struct ilcc2_handle {
   cudaStream_t work_stream[kWorkStreams] = {};
   cudaEvent_t ev_work_done[kWorkStreams] = {};
   int e2e_chunk_frames = 256;
+  int dev_chunks = 1;        // > 1 (ILCC2_DEV_CHUNKS): device-resident batches are cut into this many concurrent chunks
   bool ev_valid = false;
   int64_t launches = 0;
   std::string error;
@@ -289,6 +290,7 @@ int ilcc2_create(const ilcc2_params* params, int device, int max_frames, int max
     A(cudaEventCreateWithFlags(&h->ev_work_done[i], cudaEventDisableTiming));
   }
   if (const char* e = getenv("ILCC2_E2E_CHUNK")) h->e2e_chunk_frames = atoi(e) > 0 ? atoi(e) : h->e2e_chunk_frames;
+  if (const char* e = getenv("ILCC2_DEV_CHUNKS")) h->dev_chunks = atoi(e) > 0 ? atoi(e) : 1;
   if (ce != cudaSuccess) {
     const int rc = fail(nullptr, ILCC2_ERR_CUDA, "ilcc2_create: %s", cudaGetErrorString(ce));
     for (void* q : h->allocs) cudaFree(q);
@@ -429,11 +431,17 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
   // and computed round-robin on private work streams, so the five kernels of chunk c overlap both the copy of the
   // following chunks and the kernels of its neighbours (a small chunk leaves most SMs idle on its own: its run
   // time is the latency of its slowest frame).  Needs page-locked host memory to actually overlap.
-  // Device buffers, profiling runs and ragged batches: one chunk on the caller's stream.
+  // Device buffers: the batch is resident, so all chunks (dev_chunks equal ones) start at once on the work streams.
+  // K5 keeps the SMs' register files full for most of its run while K2-K4 are latency-bound kernels that need few
+  // resources per frame: with the chunks staggered, K1-K4 of one chunk run in the issue slots and the CTA slots that K5
+  // of the chunks before it leaves free (its tail, above all), instead of in front of it with the machine mostly idle.
+  // CTA / team sizes are chosen for the whole call's frames (load_frames), which are all in flight together.
+  // Profiling runs and ragged host batches: one chunk on the caller's stream.
   // Chunk schedule: equal chunks of e2e_chunk_frames, except that the batch ENDS with two short chunks (3/4 and 1/4
   // of a chunk).  After the last copy only the last chunk's kernels remain, and K5's run time is the latency of its
   // slowest solve, which launch_board_fit shortens for small launches by putting more warps on each solve.
   std::vector<int> cb, cn;  // first frame / frame count of every chunk
+  bool dev_chunked = false;
   if (mem_kind == ILCC2_MEM_HOST && !prof && !debug_sync && !frame_offsets && n_frames > h->e2e_chunk_frames) {
     int C = h->e2e_chunk_frames;
     while ((n_frames + C - 1) / C + 2 > ilcc2_handle::kMaxChunks) C *= 2;
@@ -457,6 +465,14 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
         f0 += nf;
       }
     }
+  } else if (mem_kind == ILCC2_MEM_DEVICE && !prof && !debug_sync && h->dev_chunks > 1 && n_frames >= 128 * h->dev_chunks) {
+    const int nc = std::min(h->dev_chunks, (int)ilcc2_handle::kMaxChunks);
+    for (int c = 0; c < nc; ++c) {
+      const int b = (int)((long long)n_frames * c / nc), e = (int)((long long)n_frames * (c + 1) / nc);
+      cb.push_back(b);
+      cn.push_back(e - b);
+    }
+    dev_chunked = true;
   } else {
     cb.push_back(0);
     cn.push_back(n_frames);
@@ -478,12 +494,17 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
       }
     }
   }
+  if (dev_chunked) {
+    CU_TRY(h, cudaEventRecord(h->ev_start, s));  // everything queued on s so far (memset, earlier calls) comes first
+    for (int i = 0; i < ilcc2_handle::kWorkStreams; ++i) CU_TRY(h, cudaStreamWaitEvent(h->work_stream[i], h->ev_start, 0));
+  }
   CU_TRY(h, stage_done(0));
   for (int c = 0; c < n_chunks; ++c) {
     w.frame_base = cb[c];
     w.n_frames = cn[c];
+    w.load_frames = dev_chunked ? n_frames : cn[c];
     cudaStream_t cs = n_chunks > 1 ? h->work_stream[c % ilcc2_handle::kWorkStreams] : s;
-    if (n_chunks > 1) CU_TRY(h, cudaStreamWaitEvent(cs, h->ev_copied[c], 0));
+    if (n_chunks > 1 && !dev_chunked) CU_TRY(h, cudaStreamWaitEvent(cs, h->ev_copied[c], 0));
     launch_roi_filter(w, h->dp, cs);
     if (n_chunks == 1) CU_TRY(h, stage_done(1));
     launch_cluster(w, h->dp, cs);
@@ -494,6 +515,7 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
     if (n_chunks == 1) CU_TRY(h, stage_done(4));
     launch_board_fit(w, h->dp, cs);
     if (n_chunks == 1) CU_TRY(h, stage_done(5));
+    CU_TRY(h, cudaGetLastError());  // a launch failure is reported before the next chunk is queued
     h->launches += kStages + 1 + (h->cap > h->ws.fit_bits_cap ? 1 : 0) + 1;
   }
   if (n_chunks > 1) {  // join the work streams back into the caller's stream

@@ -77,6 +77,8 @@ struct Workspace {
   const int8_t* pdelta;        // nullable
   int n_frames;                // frames in THIS launch (a chunk of the call's batch)
   int frame_base;              // first frame of the chunk; kernels process frames frame_base + blockIdx.x
+  int load_frames;             // frames in flight on the device at the same time (the whole call when its chunks run
+                               // concurrently, else n_frames): what CTA sizes / K5 team sizes are chosen for
   int cap;                     // per-frame capacity R of the ROI-sized arrays
   // scratch
   float4* roi_pts;             // [F][R] ROI points (x,y,z,intensity), input order

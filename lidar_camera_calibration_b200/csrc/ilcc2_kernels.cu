@@ -258,7 +258,7 @@ static void launch_roi_filter_nt(const Workspace& w, const DevParams& p, cudaStr
 }
 
 void launch_roi_filter(const Workspace& w, const DevParams& p, cudaStream_t s) {
-  if (w.n_frames >= 4 * w.num_sms)
+  if (w.load_frames >= 4 * w.num_sms)
     launch_roi_filter_nt<128>(w, p, s);
   else
     launch_roi_filter_nt<kRoiThreads>(w, p, s);
@@ -1300,6 +1300,9 @@ void launch_pca_gray(const Workspace& w, const DevParams& p, cudaStream_t s) {
 // frame that finishes second picks the lower final cost and emits the corners (to the caller's buffers and to the
 // gather targets of the other ranks, if any).
 // ------------------------------------------------------------------------------------------------
+#ifndef FIT_PAIR
+#define FIT_PAIR 1
+#endif
 struct VbModel {
   int tlw;
   double Wd, Hd, g, inv_g, wg2, hg2, ha, hb, two_ha;
@@ -1897,14 +1900,17 @@ enum { TERM_MAX_ITER = 0, TERM_GRADIENT = 1, TERM_PARAMETER = 2, TERM_FUNCTION =
 // run two reductions ahead of its team mates.  (An immediate barrier id: with a register id ptxas reserves all 16
 // named barriers for the CTA, and the barrier pool of the SM then caps the number of resident CTAs.)
 template <int NQ, int T>
-__device__ __forceinline__ void team_sum(double (&v)[NQ], double* slots /* [2][T][9] */, int wt, int lane, int& parity) {
+__device__ __forceinline__ void team_sum(double (&v)[NQ], double* slots /* [2][T][9] */, int wt, int lane, int& parity, int team) {
   if (T == 1) return;
   double* buf = slots + parity * (T * 9);
   if (lane == 0) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q) buf[wt * 9 + q] = v[q];
   }
-  asm volatile("bar.sync 1, %0;" ::"n"(32 * T) : "memory");
+  if (team == 0)  // the two teams of a CTA (one per colour hypothesis) synchronise independently
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * T) : "memory");
+  else
+    asm volatile("bar.sync 2, %0;" ::"n"(32 * T) : "memory");
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     double t = buf[q];
@@ -1950,7 +1956,7 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
   const int n = Fp->n;
   const VbModel M = *Mp;
   const bool oob = oob_i != 0;
-  const int wt = threadIdx.x >> 5;  // warp of the team
+  const int wt = (threadIdx.x >> 5) % T, team = (threadIdx.x >> 5) / T;  // warp of the team; team of the CTA
   int parity = *parity_io;
   const int team_cap = Fp->team_cap;  // points per chunk: each warp of the team classifies / evaluates its share
 
@@ -2012,7 +2018,7 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
       if (k0 + team_cap < n) __syncwarp();
     }
     double cc1[1] = {warp_butterfly(a[0])};
-    team_sum<1, T>(cc1, slots, wt, lane, parity);
+    team_sum<1, T>(cc1, slots, wt, lane, parity, team);
     const double cc = cc1[0];
     n_evals++;
 #ifdef FIT_TIMING
@@ -2049,7 +2055,7 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
       }
 #pragma unroll
       for (int q = 0; q < 9; ++q) a[q] = warp_butterfly(a[q]);
-      team_sum<9, T>(a, slots, wt, lane, parity);
+      team_sum<9, T>(a, slots, wt, lane, parity, team);
       g[0] = a[0];
       g[1] = a[1];
       g[2] = a[2];
@@ -2177,7 +2183,7 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
 #ifdef FIT_TIMING
   t_scalar += clock64() - t0;
   if (lane == 0) {
-    if ((threadIdx.x >> 5) == 0 && (blockIdx.x & 1) == 0) {
+    if ((threadIdx.x >> 5) == 0 && (FIT_PAIR || (blockIdx.x & 1) == 0)) {
       atomicAdd(&Fp->timing[0], (float)t_cls * 1e-3f);
       atomicAdd(&Fp->timing[1], (float)(t_eval - t_cls) * 1e-3f);
       atomicAdd(&Fp->timing[2], (float)t_jac * 1e-3f);
@@ -2258,21 +2264,30 @@ __device__ __forceinline__ void gather_store_status(const Workspace& w, int f, i
   for (int t = 0; t < w.n_targets; ++t) w.gather_status[t][w.gather_slot_base + f] = st;
 }
 
+// FIT_PAIR = 1: one CTA per FRAME holding two teams of T warps, one per colour hypothesis (auto mode), that run their
+// solves independently (a named barrier each) on the same points: the frame's points are then resident in the SM's L1
+// once instead of once per hypothesis on two different SMs (L1 hit rate of the point loads 69 % -> see profiles/), each
+// CTA carries one cheap (right colour phase) and one expensive (wrong phase: half of the points mismatch) solve, and the
+// CTA-wide barrier at the end replaces the global-memory handshake between the two CTAs of a frame.
+// FIT_PAIR = 0: one CTA per (frame, hypothesis) as in round 1.
 template <bool SMEM, int T>
-__global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) board_fit_kernel(const Workspace w, const DevParams p) {
+__global__ void __launch_bounds__(32 * T * (FIT_PAIR ? 2 : 1), (SMEM ? FIT_WARPS_PER_SM : 8) / (T * (FIT_PAIR ? 2 : 1)))
+    board_fit_kernel(const Workspace w, const DevParams p) {
   using IdxT = typename std::conditional<SMEM, uint16_t, uint32_t>::type;
-  constexpr int kThreads = 32 * T;
+  constexpr int kTeams = FIT_PAIR ? 2 : 1;
+  constexpr int kWarps = T * kTeams, kThreads = 32 * kWarps;
   extern __shared__ unsigned char fit_sm[];
   __shared__ double s_x[2][3];
   __shared__ double s_cost[2];
-  __shared__ float s_ext[T][2];
-  __shared__ double s_red[2 * T * 9];  // team_sum slots: [parity][warp][9]
+  __shared__ float s_ext[kWarps][2];
+  __shared__ double s_red[kTeams * 2 * T * 9];  // team_sum slots: [team][parity][warp][9]
   __shared__ int s_last;
-  __shared__ ScalarWs s_ws[T];
+  __shared__ ScalarWs s_ws[kWarps];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int fblock = blockIdx.x >> 1;
-  const int hyp_cta = blockIdx.x & 1;
+  const int team_of_cta = kTeams == 2 ? warp / T : 0;
+  const int fblock = kTeams == 2 ? blockIdx.x : blockIdx.x >> 1;
+  const int hyp_cta = kTeams == 2 ? team_of_cta : (blockIdx.x & 1);
   const int f = w.fit_order[w.frame_base + fblock];  // big frames first (fit_order_kernel)
   ilcc2_diag* d = w.diag + f;
   float* corners = w.corners + (size_t)f * p.ncorners * 3;
@@ -2280,7 +2295,7 @@ __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) boa
   const int n = w.opt_count[f];
   if (st == ILCC2_OK && (n <= w.fit_bits_cap) != SMEM) return;  // the other instantiation owns this frame
   if (st != ILCC2_OK) {
-    if (SMEM && hyp_cta == 0) {
+    if (SMEM && (kTeams == 2 || hyp_cta == 0)) {
       for (int i = tid; i < p.ncorners * 3; i += kThreads) {
         corners[i] = NAN;
         gather_store_corner(w, f, p.ncorners, i, NAN);
@@ -2294,16 +2309,16 @@ __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) boa
   }
   const unsigned flags = w.flags ? (unsigned)w.flags[f] : w.default_flags;
   const bool autom = (flags & ILCC2_FLAG_AUTO) != 0;
-  if (!autom && hyp_cta == 1) return;  // manual mode: one CTA runs the requested hypotheses in sequence
+  if (kTeams == 1 && !autom && hyp_cta == 1) return;  // manual mode: one CTA runs the requested hypotheses in sequence
   const float2* gyz = w.opt_yz + (size_t)f * w.cap;
   const uint8_t* gwh = w.opt_white + (size_t)f * w.cap;
   FitPts<IdxT> F;
   F.n = n;
   uint32_t* wbits;
   if (SMEM) {
-    // shared memory holds the two candidate lists (16-bit indices) and the colour bits; the points themselves are
-    // read through L1 (a frame's optimiser points are ~20 KB and 7 frames share an SM), which keeps the CTA's
-    // shared-memory footprint at 13 KB so that registers, not shared memory, bound the residency.
+    // shared memory holds the two candidate lists (16-bit indices) of every warp and the colour bits; the points
+    // themselves are read through L1 (a frame's optimiser points are ~15 KB), which keeps the shared-memory footprint
+    // small so that registers, not shared memory, bound the residency.
     F.bits_bytes = (int)sizeof(uint32_t) * (w.fit_bits_cap / 32);
     IdxT* lists = reinterpret_cast<IdxT*>(fit_sm + F.bits_bytes);
     F.team_cap = w.fit_team_cap;
@@ -2316,12 +2331,12 @@ __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) boa
     wbits = g;
     F.yz = gyz;
     F.bits_bytes = 0;
-    F.list = reinterpret_cast<IdxT*>(g + (w.cap + 31) / 32 + (size_t)(hyp_cta * T + warp) * w.cap);
+    F.list = reinterpret_cast<IdxT*>(g + (w.cap + 31) / 32 + (size_t)(kTeams == 2 ? warp : hyp_cta * T + warp) * w.cap);
     F.list_cap = w.cap;
     F.team_cap = w.cap;
   }
   float ymax = 0.f, zmax = 0.f;
-  for (int base = warp * 32; base < n; base += kThreads) {  // stage points; colour flags -> one bit per point
+  for (int base = warp * 32; base < n; base += kThreads) {  // stage: colour flags -> one bit per point; extent
     const int k = base + lane;
     const bool v = k < n;
     const float2 q = v ? gyz[k] : make_float2(0.f, 0.f);
@@ -2359,17 +2374,16 @@ __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) boa
   M.two_ha = 2.0 * p.huber_a;
   {
     float ym = 0.f, zm = 0.f;
-    for (int i = 0; i < T; ++i) {
+    for (int i = 0; i < kWarps; ++i) {
       ym = fmaxf(ym, s_ext[i][0]);
       zm = fmaxf(zm, s_ext[i][1]);
     }
     M.ymax_zmax = ym + zm;
   }
-  const int wt = warp;
-  const int team = hyp_cta;  // colour hypothesis this CTA solves in auto mode
-  {
-    const int h_first = autom ? team : 0;
-    const int h_last = autom ? team : ((flags & ILCC2_FLAG_TOPLEFT_WHITE) ? 1 : 0);
+  const int wt = warp % T;
+  if (autom || team_of_cta == 0) {  // manual mode: team 0 runs the requested hypotheses in sequence, team 1 waits
+    const int h_first = autom ? hyp_cta : 0;
+    const int h_last = autom ? hyp_cta : ((flags & ILCC2_FLAG_TOPLEFT_WHITE) ? 1 : 0);
     double x[3] = {0.0, 0.0, 0.0};
     int parity = 0;
     for (int h = h_first; h <= h_last; ++h) {  // manual mode: 'd' warm-starts hypothesis 1 from hypothesis 0
@@ -2379,7 +2393,8 @@ __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) boa
 #pragma unroll 1
       for (int phase = 0; phase < 2; ++phase) {  // useOutofBoard first, then without (LidarCornersEst.cpp:402-409); one call site
         int it = 0;
-        const int term = solve_tr<IdxT, T>(&F, &M, 1 - phase, p.max_solver_iter, lane, x, &fc, &it, &evals, s_red, &parity, &s_ws[warp]);
+        const int term = solve_tr<IdxT, T>(&F, &M, 1 - phase, p.max_solver_iter, lane, x, &fc, &it, &evals,
+                                           s_red + team_of_cta * (2 * T * 9), &parity, &s_ws[warp]);
         if (lane == 0 && wt == 0) {
           d->iters[h][phase] = it;
           d->term[h][phase] = term;
@@ -2398,7 +2413,7 @@ __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) boa
     }
   }
   __syncthreads();
-  if (autom) {
+  if (kTeams == 1 && autom) {
     // the CTA of the other hypothesis publishes through diag; whichever CTA arrives second finishes the frame
     if (tid == 0) {
       __threadfence();
@@ -2450,7 +2465,8 @@ __global__ void __launch_bounds__(32 * T, (SMEM ? FIT_WARPS_PER_SM : 8) / T) boa
 }
 
 size_t fit_smem_bytes(const Workspace& w, int team) {
-  return sizeof(uint32_t) * (w.fit_bits_cap / 32) + sizeof(uint16_t) * (size_t)team * fit_list_cap(w.fit_team_cap, team);
+  return sizeof(uint32_t) * (w.fit_bits_cap / 32) +
+         sizeof(uint16_t) * (size_t)team * (FIT_PAIR ? 2 : 1) * fit_list_cap(w.fit_team_cap, team);
 }
 
 // Team size for a launch of `frames` frames: the largest T in {2, 4, 8} for which all 2 * frames CTAs are resident at
@@ -2469,18 +2485,19 @@ int fit_team_size(int frames, int num_sms) {
 
 template <int T>
 static void launch_fit_smem(const Workspace& w, const DevParams& p, cudaStream_t s) {
-  board_fit_kernel<true, T><<<2 * w.n_frames, 32 * T, fit_smem_bytes(w, T), s>>>(w, p);
+  board_fit_kernel<true, T><<<(FIT_PAIR ? 1 : 2) * w.n_frames, 32 * T * (FIT_PAIR ? 2 : 1), fit_smem_bytes(w, T), s>>>(w, p);
 }
 
 void launch_board_fit(const Workspace& w, const DevParams& p, cudaStream_t s) {
   fit_order_kernel<<<1, 1024, 0, s>>>(w, w.num_sms);
-  switch (fit_team_size(w.n_frames, w.num_sms)) {
+  switch (fit_team_size(w.load_frames, w.num_sms)) {
     case 1: launch_fit_smem<1>(w, p, s); break;
     case 2: launch_fit_smem<2>(w, p, s); break;
     case 4: launch_fit_smem<4>(w, p, s); break;
     default: launch_fit_smem<8>(w, p, s); break;
   }
-  if (w.cap > w.fit_bits_cap) board_fit_kernel<false, kFitGlobalTeam><<<2 * w.n_frames, 32 * kFitGlobalTeam, 0, s>>>(w, p);
+  if (w.cap > w.fit_bits_cap)
+    board_fit_kernel<false, kFitGlobalTeam><<<(FIT_PAIR ? 1 : 2) * w.n_frames, 32 * kFitGlobalTeam * (FIT_PAIR ? 2 : 1), 0, s>>>(w, p);
 }
 
 cudaError_t configure_kernels() {
@@ -2488,16 +2505,16 @@ cudaError_t configure_kernels() {
   e = cudaFuncSetAttribute(cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem_bytes());
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(board_fit_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(sizeof(uint32_t) * (kFitBitsCapBig / 32) + sizeof(uint16_t) * kFitTeamCapBig));
+                           (int)(sizeof(uint32_t) * (kFitBitsCapBig / 32) + sizeof(uint16_t) * kFitTeamCapBig * (FIT_PAIR ? 2 : 1)));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(board_fit_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(sizeof(uint32_t) * (kFitBitsCapBig / 32) + sizeof(uint16_t) * kFitTeamCapBig));
+                           (int)(sizeof(uint32_t) * (kFitBitsCapBig / 32) + sizeof(uint16_t) * kFitTeamCapBig * (FIT_PAIR ? 2 : 1)));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(board_fit_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(sizeof(uint32_t) * (kFitBitsCapBig / 32) + sizeof(uint16_t) * kFitTeamCapBig));
+                           (int)(sizeof(uint32_t) * (kFitBitsCapBig / 32) + sizeof(uint16_t) * kFitTeamCapBig * (FIT_PAIR ? 2 : 1)));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(board_fit_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(sizeof(uint32_t) * (kFitBitsCapBig / 32) + sizeof(uint16_t) * kFitTeamCapBig));
+                           (int)(sizeof(uint32_t) * (kFitBitsCapBig / 32) + sizeof(uint16_t) * kFitTeamCapBig * (FIT_PAIR ? 2 : 1)));
   return e;
 }
 

@@ -42,9 +42,17 @@ if sys.argv[1] == "--child":
                f"max|dcorner|={np.abs(c[ok] - z['c'][ok]).max():.2e} max|dtheta_t|={np.abs(th[ok] - z['th'][ok]).max():.2e}")
     else:
         np.savez(ref, st=st, c=c, it=it, th=th)
-    print(f"{name:>14s} F={F} step={e0.elapsed_time(e1) / R:.3f} ms  " + " ".join(f"{k}={v:.3f}" for k, v in acc.items()) + msg, flush=True)
+    print(f"{name:>28s} F={F} step={e0.elapsed_time(e1) / R:.3f} ms  " + " ".join(f"{k}={v:.3f}" for k, v in acc.items()) + msg, flush=True)
     sys.exit(0)
 F = int(sys.argv[1])
 for name in sys.argv[2:]:
-    env = dict(os.environ, ILCC2_LIB=os.path.join(ROOT, "build_variants", f"lib_{name}.so"))
+    # name[@ENV=VAL[@ENV=VAL...]]; the name "tree" is the in-tree build
+    lib, *assign = name.split("@")
+    path = os.path.join(ROOT, "build_variants", f"lib_{lib}.so")
+    env = dict(os.environ)
+    if lib != "tree":
+        env["ILCC2_LIB"] = path
+    for a in assign:
+        k, v = a.split("=", 1)
+        env[k] = v
     subprocess.run([sys.executable, __file__, "--child", name, str(F)], env=env)
