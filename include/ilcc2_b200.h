@@ -48,7 +48,10 @@ enum {
   ILCC2_PLANE_TOO_SMALL = 3,      /* fewer plane inliers than min_board_points (online gate, :111) or < 3 */
   ILCC2_DEGENERATE_INTENSITY = 4, /* max==min (division by zero, :235) or the mode walk runs off the map (:266-282) */
   ILCC2_NO_OPT_POINTS = 5,        /* every board point fell in the gray zone */
-  ILCC2_RANSAC_FAILED = 6         /* no non-degenerate 3-point sample */
+  ILCC2_RANSAC_FAILED = 6,        /* no non-degenerate 3-point sample */
+  ILCC2_ROI_CAPACITY = 7          /* the frame's ROI holds more points than the handle's roi_capacity, or more frames of
+                                     the call needed the global-memory clustering tables than the handle holds
+                                     (ilcc2_create_sized); never with ilcc2_create's defaults */
 };
 
 /* ---- per-frame flags = the reference's key presses ---- */
@@ -119,10 +122,18 @@ void ilcc2_default_params(ilcc2_params* p);
 int ilcc2_set_chessboard_param(ilcc2_params* p, const char* cam_yaml_path);
 
 /* Creates a handle that owns all device scratch for up to max_frames frames of up to
- * max_points_per_frame points each (no allocation happens per call afterwards).
+ * max_points_per_frame points each, including the staging ring that host batches stream through (no allocation per
+ * call afterwards; the first call with PAGEABLE host memory adds a page-locked ring and copy threads, once).
  * One handle per (GPU, stream); a handle is not thread-safe. */
 int ilcc2_create(const ilcc2_params* params, int device, int max_frames, int max_points_per_frame,
                  ilcc2_handle** out);
+/* Same, with the scratch sized for the caller's data instead of the worst case: the ROI-sized arrays (41 bytes per
+ * entry and frame) hold roi_capacity points per frame (0 = max_points_per_frame: every point may survive setROI; the
+ * bundled VLP-16 bags keep 2.9-5.4 k of 24 k points), and the global-memory clustering tables that ROIs above 4096
+ * points (or very sparse ones) use exist for overflow_frames frames of a call (0 = every frame when roi_capacity >
+ * 4096, else max_frames / 8).  A frame beyond either limit reports ILCC2_ROI_CAPACITY; nothing is truncated. */
+int ilcc2_create_sized(const ilcc2_params* params, int device, int max_frames, int max_points_per_frame,
+                       int roi_capacity, int overflow_frames, ilcc2_handle** out);
 int ilcc2_destroy(ilcc2_handle* h);
 
 /* Last error text of the handle (or of the last failed ilcc2_create when h == NULL). */
@@ -175,12 +186,38 @@ int ilcc2_save_corners2txt(const float* corners_xyz, int n_corners, const char* 
 /* Multi-GPU: the all-gather of the per-frame corners fused into the kernel that produces them.
  * After this call every ilcc2_extract_corners of the handle ALSO stores frame f's corners and status into each target at
  * frame slot slot_base + f: corners_targets[t] is a device-accessible float[total_frames][n_corners][3],
- * status_targets[t] an int32[total_frames].  Targets are peer-mapped buffers of the ranks of one NVLink/NVSwitch domain
- * (n_targets = world size; e.g. torch symmetric memory or cudaIpc mappings) or one multicast (NVLS) mapping of such a
- * buffer (n_targets = 1).  The caller separates producers and consumers with one barrier (no data-path collective).
+ * status_targets[t] an int32[total_frames].
+ *   target_kind ILCC2_GATHER_PEER       n_targets = world size: peer-mapped buffers of the ranks of one NVLink / NVSwitch
+ *                                       domain (torch symmetric memory, cudaIpc mappings, peer-enabled pointers): plain
+ *                                       stores, one per target.
+ *               ILCC2_GATHER_MULTICAST  n_targets = 1: ONE multicast (NVLS) mapping of such a buffer; stored to with
+ *                                       multimem.st, NVSwitch fans the store out to every rank.
+ * The caller separates producers and consumers with one barrier per step (no data-path collective) AND must make sure
+ * that no rank starts the next step's extract into a buffer that another rank is still reading: alternate between two
+ * buffers (call this function before every step; it only updates the handle) or add a second barrier after the read.
  * n_targets = 0 switches it off.  At most 8 targets. */
+#define ILCC2_GATHER_PEER      0
+#define ILCC2_GATHER_MULTICAST 1
 int ilcc2_set_gather_targets(ilcc2_handle* h, int n_targets, float* const* corners_targets,
-                             int32_t* const* status_targets, int slot_base);
+                             int32_t* const* status_targets, int slot_base, int target_kind);
+
+/* The same for a C / C++ host that runs one rank per GPU over an NCCL communicator (what a multi-GPU build of
+ * ilcc2/test/calib_lidar_cam.cpp:116-165, the consumer of every frame's corners, would hold): allocates a double-
+ * buffered gather buffer for total_frames frames on this rank, exchanges cudaIpc handles (or, between ranks of one
+ * process, peer-enabled pointers) through ncclAllGather on `nccl_comm` (an ncclComm_t; NCCL is resolved from the host
+ * process at run time, this library does not link it) and points the fused stores of K5 at every rank's buffer.  If any
+ * rank cannot map a peer, all ranks fall back to a plain ncclAllGather inside ilcc2_gather_sync.  Collective: every
+ * rank of the communicator calls it; slot_base = this rank's first frame in the gathered order.
+ *   ilcc2_gather_sync     after the step's ilcc2_extract_corners (ILCC2_MEM_DEVICE, same stream): the barrier between
+ *                         producers and consumers (one ncclAllReduce of an int) -- or the ncclAllGather of the
+ *                         fallback -- enqueued on `stream`; returns the device pointers that hold ALL ranks' corners /
+ *                         status once `stream` reaches this point, and switches the handle to the other half of the
+ *                         double buffer for the next step.
+ *   ilcc2_gather_is_fused 1: K5 stores over NVLink; 0: NCCL fallback. */
+int ilcc2_gather_setup_nccl(ilcc2_handle* h, void* nccl_comm, int total_frames, int slot_base);
+int ilcc2_gather_sync(ilcc2_handle* h, const float** corners_all, const int32_t** status_all, void* stream);
+int ilcc2_gather_is_fused(const ilcc2_handle* h);
+int ilcc2_gather_teardown(ilcc2_handle* h);
 
 /* Frame sharding across ranks (one process per GPU): contiguous blocks. */
 void ilcc2_shard_range(int n_frames, int world_size, int rank, int* begin, int* count);

@@ -80,7 +80,9 @@ class Optimization {
 
   void order_corners(std::vector<Vector3d>& lidar_corners, std::vector<Point2d>& image_corners, Size board,
                      const Isometry3d& T_axis_roughly) {
-    const int nc = board.width * board.height, frames = (int)(lidar_corners.size() / nc);
+    const int nc = board.width * board.height, frames = nc > 0 ? (int)(lidar_corners.size() / nc) : 0;
+    if (nc <= 0 || lidar_corners.size() != image_corners.size() || lidar_corners.size() != (size_t)frames * nc)
+      throw std::invalid_argument("order_corners: lidar / image corner counts must be equal and a multiple of the board size");
     std::vector<float> lf(lidar_corners.size() * 3);
     for (size_t i = 0; i < lidar_corners.size(); ++i)
       for (int k = 0; k < 3; ++k) lf[3 * i + k] = (float)lidar_corners[i][k];  // the files hold floats

@@ -59,6 +59,7 @@ class LidarCornersEst {
   }
   ~LidarCornersEst() {
     if (h_) ilcc2_destroy(h_);
+    if (h_online_) ilcc2_destroy(h_online_);
   }
   LidarCornersEst(const LidarCornersEst&) = delete;
   LidarCornersEst& operator=(const LidarCornersEst&) = delete;
@@ -71,6 +72,10 @@ class LidarCornersEst {
     if (h_) {
       ilcc2_destroy(h_);
       h_ = nullptr;
+    }
+    if (h_online_) {
+      ilcc2_destroy(h_online_);
+      h_online_ = nullptr;
     }
     return true;
   }
@@ -131,6 +136,43 @@ class LidarCornersEst {
     return true;
   }
 
+  // LidarCornersEst.cpp:72-115, the streaming variant driven by ilcc2/test/lidar_chessboard_online.cpp:91-99: no
+  // box ROI (the whole cloud is clustered), cluster tolerance 0.10, the plane of the cluster that holds the nearest
+  // neighbour of `point`; false when that plane has fewer than 500 points or the neighbour lies in no kept cluster
+  // (find_board == false, :111-112) -- outcloud then still holds the plane of the largest cluster, as in the
+  // reference.  Deviation: points farther than online_extent (default 25 m per axis) from `point` are ignored (the
+  // cell hash of the clustering kernel spans at most 1023 cells of 0.055 m per axis).
+  bool get_chessboard_by_point(myPointCloud::Ptr incloud, myPointCloud::Ptr& outcloud, myPoint point) {
+    if (!incloud) throw std::logic_error("get_chessboard_by_point: null cloud");
+    if (!h_online_) {
+      ilcc2_params p = params_;
+      p.roi_half_x = p.roi_half_y = p.roi_half_z = online_extent;
+      p.cluster_tolerance = 0.1f;   // :79
+      p.min_board_points = 500;     // :111
+      if (ilcc2_create(&p, device_, 1, max_points_, &h_online_) != ILCC2_SUCCESS)
+        throw std::runtime_error(std::string("ilcc2_create: ") + ilcc2_last_error(nullptr));
+    }
+    const int ncorn = (params_.cells_x - 1) * (params_.cells_y - 1);
+    std::vector<float> corners((size_t)ncorn * 3);
+    const float click[3] = {point.x, point.y, point.z};
+    int32_t st = 0;
+    ilcc2_diag dg{};
+    const int rc = ilcc2_extract_corners(h_online_, incloud->points.data(), 1, (int)incloud->size(), nullptr, 32, 0, 4, 8, 16,
+                                         ILCC2_MEM_HOST, click, nullptr, ILCC2_FLAG_AUTO, nullptr, corners.data(), &st, &dg,
+                                         nullptr);
+    if (rc != ILCC2_SUCCESS) throw std::runtime_error(std::string("ilcc2_extract_corners: ") + ilcc2_last_error(h_online_));
+    online_diag_ = dg;
+    outcloud.reset(new myPointCloud);
+    std::vector<int32_t> idx(incloud->size());
+    const int n = ilcc2_fetch_indices(h_online_, 0, 2, idx.data(), (int)idx.size());
+    for (int i = 0; i < n && i < (int)idx.size(); ++i) outcloud->points.push_back(incloud->points[idx[i]]);
+    const bool no_plane = st == ILCC2_NO_POINTS_IN_ROI || st == ILCC2_NO_CLUSTER || st == ILCC2_RANSAC_FAILED ||
+                          st == ILCC2_PLANE_TOO_SMALL || st == ILCC2_ROI_CAPACITY;
+    return !no_plane && outcloud->size() >= 500 && dg.click_in_cluster != 0;
+  }
+  const ilcc2_diag& online_diag() const { return online_diag_; }
+  float online_extent = 25.0f;
+
   int status() const { return status_; }
   const ilcc2_diag& diag() const { return diag_; }
   ilcc2_params& params() { return params_; }
@@ -169,6 +211,8 @@ class LidarCornersEst {
   int device_, max_points_;
   ilcc2_params params_;
   ilcc2_handle* h_ = nullptr;
+  ilcc2_handle* h_online_ = nullptr;
+  ilcc2_diag online_diag_{};
   myPointCloud::Ptr cloud_;
   bool ran_ = false;
   int32_t status_ = ILCC2_NO_POINTS_IN_ROI;

@@ -19,7 +19,8 @@ EXPORTS = [
     "ilcc2_pnp_create", "ilcc2_pnp_destroy", "ilcc2_pnp_last_error", "ilcc2_pnp_launch_count", "ilcc2_axis_roughly",
     "ilcc2_pnp_order_corners", "ilcc2_pnp_solve", "ilcc2_compose_extrinsic", "ilcc2_extrinsic2bin",
     "ilcc2_read_cam_corners", "ilcc2_read_lidar_corners", "ilcc2_read_camera_yaml", "ilcc2_project_points",
-    "ilcc2_set_gather_targets",
+    "ilcc2_set_gather_targets", "ilcc2_create_sized", "ilcc2_gather_setup_nccl", "ilcc2_gather_sync",
+    "ilcc2_gather_is_fused", "ilcc2_gather_teardown",
 ]
 
 
@@ -75,6 +76,8 @@ def load() -> C.CDLL:
     L.ilcc2_set_chessboard_param.argtypes = [C.POINTER(Params), C.c_char_p]
     L.ilcc2_create.restype = C.c_int
     L.ilcc2_create.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.ilcc2_create_sized.restype = C.c_int
+    L.ilcc2_create_sized.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.ilcc2_destroy.restype = C.c_int
     L.ilcc2_destroy.argtypes = [C.c_void_p]
     L.ilcc2_last_error.restype = C.c_char_p
@@ -98,7 +101,15 @@ def load() -> C.CDLL:
     L.ilcc2_shard_range.restype = None
     L.ilcc2_shard_range.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.ilcc2_set_gather_targets.restype = C.c_int
-    L.ilcc2_set_gather_targets.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]
+    L.ilcc2_set_gather_targets.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int]
+    L.ilcc2_gather_setup_nccl.restype = C.c_int
+    L.ilcc2_gather_setup_nccl.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.ilcc2_gather_sync.restype = C.c_int
+    L.ilcc2_gather_sync.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
+    L.ilcc2_gather_is_fused.restype = C.c_int
+    L.ilcc2_gather_is_fused.argtypes = [C.c_void_p]
+    L.ilcc2_gather_teardown.restype = C.c_int
+    L.ilcc2_gather_teardown.argtypes = [C.c_void_p]
     L.ilcc2_pnp_create.restype = C.c_int
     L.ilcc2_pnp_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     L.ilcc2_pnp_destroy.restype = C.c_int

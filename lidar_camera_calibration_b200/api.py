@@ -23,8 +23,9 @@ FLAG_INVERSE = 2
 FLAG_AUTO = 4
 MEM_HOST, MEM_DEVICE = 0, 1
 STATUS_NAMES = {0: "OK", 1: "NO_POINTS_IN_ROI", 2: "NO_CLUSTER", 3: "PLANE_TOO_SMALL",
-                4: "DEGENERATE_INTENSITY", 5: "NO_OPT_POINTS", 6: "RANSAC_FAILED"}
-STAGES = ("roi_filter", "cluster", "plane", "pca_gray", "board_fit")
+                4: "DEGENERATE_INTENSITY", 5: "NO_OPT_POINTS", 6: "RANSAC_FAILED", 7: "ROI_CAPACITY"}
+GATHER_PEER, GATHER_MULTICAST = 0, 1
+STAGES = ("roi_filter", "cluster", "plane_pca", "board_fit")
 
 
 class Ilcc2Error(RuntimeError):
@@ -69,7 +70,9 @@ def _is_torch(x) -> bool:
 class CornerExtractor:
     """Owns one ilcc2_handle (device scratch for max_frames x max_points_per_frame)."""
 
-    def __init__(self, max_frames: int, max_points_per_frame: int, params: Params | None = None, device: int = 0):
+    def __init__(self, max_frames: int, max_points_per_frame: int, params: Params | None = None, device: int = 0,
+                 roi_capacity: int = 0, overflow_frames: int = 0):
+        """roi_capacity / overflow_frames: ilcc2_create_sized (0 = worst-case sizing, as ilcc2_create)."""
         self._L = _lib.load()
         self.params = params or default_params()
         self.device = device
@@ -77,7 +80,8 @@ class CornerExtractor:
         self.max_points = max_points_per_frame
         self.n_corners = (self.params.cells_x - 1) * (self.params.cells_y - 1)
         h = C.c_void_p()
-        rc = self._L.ilcc2_create(C.byref(self.params), device, max_frames, max_points_per_frame, C.byref(h))
+        rc = self._L.ilcc2_create_sized(C.byref(self.params), device, max_frames, max_points_per_frame,
+                                        int(roi_capacity), int(overflow_frames), C.byref(h))
         if rc != 0:
             raise Ilcc2Error(f"ilcc2_create failed ({rc}): {self._L.ilcc2_last_error(None).decode()}")
         self._h = h
@@ -162,14 +166,15 @@ class CornerExtractor:
         return status, corners
 
     # ---- introspection of the last call ----
-    def set_gather_targets(self, corner_ptrs, status_ptrs, slot_base: int):
+    def set_gather_targets(self, corner_ptrs, status_ptrs, slot_base: int, kind: int = GATHER_PEER):
         """ilcc2_set_gather_targets: K5 also stores every frame's corners / status into these device-accessible
-        buffers (peer mappings of the other ranks, or one multicast mapping) at frame slot slot_base + f."""
+        buffers (kind GATHER_PEER: peer mappings of the ranks; GATHER_MULTICAST: one multicast mapping, stored to with
+        multimem.st) at frame slot slot_base + f."""
         n = len(corner_ptrs)
         assert n == len(status_ptrs)
         ca = (C.c_void_p * max(n, 1))(*[int(p) for p in corner_ptrs])
         sa = (C.c_void_p * max(n, 1))(*[int(p) for p in status_ptrs])
-        self._check(self._L.ilcc2_set_gather_targets(self._h, n, ca, sa, int(slot_base)))
+        self._check(self._L.ilcc2_set_gather_targets(self._h, n, ca, sa, int(slot_base), int(kind)))
 
     def fetch_indices(self, frame: int, which: int) -> np.ndarray:
         """which: 0 m_cloud_ROI, 1 chosen cluster, 2 m_cloud_chessboard -- original point indices of `frame`."""

@@ -90,7 +90,10 @@ struct Workspace {
   int* brd_idx;                // [F][R] plane inliers, ROI indices ascending
   int* brd_count;              // [F]
   int* tmp_idx;                // [F][R] RANSAC permutation, then inliers of the sample model
-  int* cl_scratch;             // [F][cl_stride] global-memory clustering tables for large ROIs
+  int* cl_scratch;             // [cl_pool_slots][cl_stride] global-memory clustering tables for large ROIs (a pool:
+                               // frames that need them take the next free slot through cl_pool_next)
+  int cl_pool_slots;
+  int* cl_pool_next;
   int cl_ts;                   // slots in the global hash table (power of two)
   long long cl_stride;
   float2* opt_yz;              // [F][R] non-gray board points in the PCA frame (y', z')
@@ -110,6 +113,7 @@ struct Workspace {
   ilcc2_diag* diag;            // [F] (always present internally)
   // multi-GPU: K5 also stores corners / status into peer-mapped gather buffers (ilcc2_set_gather_targets)
   int n_targets;               // 0 = off; else entries of gather_corners / gather_status in use
+  int gather_multicast;        // 1: target 0 is a multicast (NVLS) mapping -> multimem.st; 0: ordinary peer pointers
   int gather_slot_base;        // frame f of this handle goes to slot gather_slot_base + f of every target
   float* gather_corners[kMaxGatherTargets];
   int32_t* gather_status[kMaxGatherTargets];
@@ -117,8 +121,7 @@ struct Workspace {
 
 void launch_roi_filter(const Workspace& w, const DevParams& p, cudaStream_t s);
 void launch_cluster(const Workspace& w, const DevParams& p, cudaStream_t s);
-void launch_plane(const Workspace& w, const DevParams& p, cudaStream_t s);
-void launch_pca_gray(const Workspace& w, const DevParams& p, cudaStream_t s);
+void launch_plane_pca(const Workspace& w, const DevParams& p, cudaStream_t s);
 void launch_board_fit(const Workspace& w, const DevParams& p, cudaStream_t s);
 cudaError_t configure_kernels();
 size_t cluster_smem_bytes();

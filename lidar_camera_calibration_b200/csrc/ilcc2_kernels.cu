@@ -3,8 +3,8 @@
 // One launch per stage over the whole batch, one CTA per frame in every stage:
 //   K1 roi_filter   setROI                     (ilcc2/src/LidarCornersEst.cpp:48-70)      HBM-bound stream
 //   K2 cluster      EuclideanCluster           (LidarCornersEst.cpp:124-153)              shared-memory hash + union-find
-//   K3 plane        getPlane                   (LidarCornersEst.cpp:190-221)              RANSAC + covariance refit
-//   K4 pca_gray     transformbyPCA + calHist   (LidarCornersEst.cpp:224-372)
+//   K3 plane        getPlane                   (LidarCornersEst.cpp:190-221)              RANSAC + covariance refit   } one launch:
+//   K4 pca_gray     transformbyPCA + calHist   (LidarCornersEst.cpp:224-372)                                          } plane_pca_kernel
 //   K5 board_fit    get_theta_t + getPCDcorners(Optimization.cpp:94-160, Optimization.h:31-107, LidarCornersEst.cpp:374-450, 501-556)
 //
 // Compiled with -fmad=false: every fp32 comparison that decides set membership (ROI box, 0.12 m linkage,
@@ -237,13 +237,14 @@ __global__ void __launch_bounds__(NT, 1024 / NT) roi_filter_kernel(const Workspa
   __syncthreads();
   if (tid == 0) {
     for (int i = 1; i < NW; ++i) best = s_key[i] < best ? s_key[i] : best;
-    const int m = total < w.cap ? total : w.cap;
+    const bool over = total > w.cap;  // more ROI points than the handle's roi_capacity: reported, nothing is truncated
+    const int m = over ? 0 : total;
     w.roi_count[f] = m;
     w.nn_key[f] = best;
     ilcc2_diag* d = w.diag + f;
-    d->n_roi = m;
+    d->n_roi = total;
     d->nn_index = m == 0 ? 0 : (int)(best & 0xffffffffull);
-    d->status = (m == 0) ? ILCC2_NO_POINTS_IN_ROI : ILCC2_OK;
+    d->status = over ? ILCC2_ROI_CAPACITY : (m == 0) ? ILCC2_NO_POINTS_IN_ROI : ILCC2_OK;
   }
 }
 
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(kClusterThreads, SMEM ? 3 : 1) cluster_kernel(
   constexpr int kEnd = (NxtT)(-1);
   extern __shared__ int sm[];
   __shared__ int s_warp[NT / 32];
-  __shared__ int s_nocc, s_nkept, s_chosen_root;
+  __shared__ int s_nocc, s_nkept, s_chosen_root, s_slot;
   __shared__ unsigned s_queue_fallback[SMEM ? 1 : (NT / 32) * kClusterQueue];  // code words
   __shared__ int s_queue_slot[SMEM ? 1 : (NT / 32) * kClusterQueue];         // slot ids (do not fit 13 bits)
 
@@ -404,7 +405,16 @@ __global__ void __launch_bounds__(kClusterThreads, SMEM ? 3 : 1) cluster_kernel(
     min_idx = reinterpret_cast<int*>(bitmap);  // bitmap + queues (>= kClusterSmemPts ints) are free by then
   } else {
     TS = w.cl_ts;
-    int* g = w.cl_scratch + (size_t)f * w.cl_stride;
+    if (tid == 0) s_slot = atomicAdd(w.cl_pool_next, 1);  // next free table of the pool
+    __syncthreads();
+    if (s_slot >= w.cl_pool_slots) {  // more overflow frames in this call than the handle holds tables for
+      if (tid == 0) {
+        d->status = ILCC2_ROI_CAPACITY;
+        w.sel_count[f] = 0;
+      }
+      return;
+    }
+    int* g = w.cl_scratch + (size_t)s_slot * w.cl_stride;
     key = g;
     head = reinterpret_cast<NxtT*>(key + TS);
     parent = head + TS;
@@ -836,7 +846,7 @@ __device__ __forceinline__ bool plane_from_3(const float4 p0, const float4 p1, c
   return true;
 }
 
-__global__ void __launch_bounds__(kPlaneThreads) plane_kernel(const Workspace w, const DevParams p) {
+__device__ __forceinline__ void plane_stage(const Workspace& w, const DevParams& p) {
   constexpr int NT = kPlaneThreads;
   __shared__ float s_model[4];
   __shared__ int s_ctrl;  // 1: score s_model, 0: stop
@@ -1056,9 +1066,6 @@ __global__ void __launch_bounds__(kPlaneThreads) plane_kernel(const Workspace w,
   }
 }
 
-void launch_plane(const Workspace& w, const DevParams& p, cudaStream_t s) {
-  plane_kernel<<<w.n_frames, kPlaneThreads, 0, s>>>(w, p);
-}
 
 // ------------------------------------------------------------------------------------------------
 // K4  pca_gray: transformbyPCA (centroid, covariance/N, eigenvectors, T = [V^T | -V^T c]) + calHist /
@@ -1074,7 +1081,7 @@ __device__ __forceinline__ void xform_pt(const float* T, float x, float y, float
   }
 }
 
-__global__ void __launch_bounds__(kPlaneThreads) pca_gray_kernel(const Workspace w, const DevParams p) {
+__device__ __forceinline__ void pca_gray_stage(const Workspace& w, const DevParams& p) {
   constexpr int NT = kPlaneThreads;
   __shared__ double s_part[6 * 128];
   __shared__ double s_out[6];
@@ -1275,8 +1282,16 @@ __global__ void __launch_bounds__(kPlaneThreads) pca_gray_kernel(const Workspace
   }
 }
 
-void launch_pca_gray(const Workspace& w, const DevParams& p, cudaStream_t s) {
-  pca_gray_kernel<<<w.n_frames, kPlaneThreads, 0, s>>>(w, p);
+// K3 + K4 in one launch: the same 128-thread CTA per frame runs the plane stage and then, on the board indices it has
+// just written (still in L1 / L2), the PCA + gray-zone stage: one launch and one pass over the frame's ROI points less.
+__global__ void __launch_bounds__(kPlaneThreads) plane_pca_kernel(const Workspace w, const DevParams p) {
+  plane_stage(w, p);
+  __syncthreads();  // brd_idx / brd_count / diag.status written by this CTA above are visible to all of its threads
+  pca_gray_stage(w, p);
+}
+
+void launch_plane_pca(const Workspace& w, const DevParams& p, cudaStream_t s) {
+  plane_pca_kernel<<<w.n_frames, kPlaneThreads, 0, s>>>(w, p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2254,14 +2269,23 @@ __global__ void __launch_bounds__(1024) fit_order_kernel(const Workspace w, int 
 #define FIT_WARPS_PER_SM 16
 #endif
 // The all-gather of SURVEY.md 8(e) fused into the producer: besides the caller's own buffers, K5 stores a frame's
-// corners and status into every gather target -- peer-mapped buffers of the other ranks (plain stores over NVLink),
-// or ONE multicast mapping that NVSwitch fans out to all ranks (multimem.st is an ordinary st.sys on such an address).
+// corners and status into every gather target -- peer-mapped buffers of the ranks (plain stores over NVLink), or ONE
+// multicast (NVLS) mapping that NVSwitch fans out to all ranks.  A multicast address may only be touched by multimem.*
+// instructions (PTX ISA: any other access to it is undefined), so that mode stores with multimem.st.
 __device__ __forceinline__ void gather_store_corner(const Workspace& w, int f, int ncorners, int i, float v) {
   const size_t at = (size_t)(w.gather_slot_base + f) * ncorners * 3 + i;
-  for (int t = 0; t < w.n_targets; ++t) w.gather_corners[t][at] = v;
+  if (w.gather_multicast) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(w.gather_corners[0] + at), "f"(v) : "memory");
+  } else {
+    for (int t = 0; t < w.n_targets; ++t) w.gather_corners[t][at] = v;
+  }
 }
 __device__ __forceinline__ void gather_store_status(const Workspace& w, int f, int32_t st) {
-  for (int t = 0; t < w.n_targets; ++t) w.gather_status[t][w.gather_slot_base + f] = st;
+  if (w.gather_multicast) {
+    asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(w.gather_status[0] + w.gather_slot_base + f), "r"(st) : "memory");
+  } else {
+    for (int t = 0; t < w.n_targets; ++t) w.gather_status[t][w.gather_slot_base + f] = st;
+  }
 }
 
 // FIT_PAIR = 1: one CTA per FRAME holding two teams of T warps, one per colour hypothesis (auto mode), that run their

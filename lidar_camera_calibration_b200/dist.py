@@ -65,11 +65,15 @@ def allgather_rows(x, world_size: int):
 class FusedGather:
     """The all-gather of the per-frame corners fused into the kernel that produces them.
 
-    Every rank owns one symmetric-memory buffer [world * F_local frames] (torch.distributed._symmetric_memory: the
-    allocations of all ranks are mapped into each other's address space over NVLink); K5 stores frame f of rank r into
-    slot r * F_local + f of EVERY rank's buffer (ilcc2_set_gather_targets) -- through the NVLS multicast mapping with
-    one store per value when the fabric offers it, else with one plain store per peer.  barrier() is the only
-    cross-rank operation of a step: a signal-pad barrier, no data moves through a collective.
+    Every rank owns a symmetric-memory buffer of TWO halves [2][world * F_local frames]
+    (torch.distributed._symmetric_memory: the allocations of all ranks are mapped into each other's address space over
+    NVLink); K5 stores frame f of rank r into slot r * F_local + f of EVERY rank's current half
+    (ilcc2_set_gather_targets) -- through the NVLS multicast mapping with one multimem.st per value when the fabric
+    offers it, else with one plain store per peer.  barrier() is the only cross-rank operation of a step: a signal-pad
+    barrier, no data moves through a collective.  It also flips to the other half for the next step, so a rank that
+    runs ahead cannot overwrite corners another rank is still reading: it reaches this half again only after the NEXT
+    barrier, which every rank enters after it has consumed this step (consume(k) precedes produce(k+1) in stream order).
+    `corners` / `status` always name the half the last barrier() completed.
 
     Raises if symmetric memory cannot be set up; callers fall back to allgather_corners (NCCL)."""
 
@@ -81,25 +85,39 @@ class FusedGather:
         self.world, self.rank, self.F, self.ncorn = world, rank, frames_local, n_corners
         total = world * frames_local
         cbytes = total * n_corners * 3 * 4
-        self.buf = symm.empty((cbytes + total * 4,), dtype=torch.uint8, device=device)
+        half = (cbytes + total * 4 + 255) // 256 * 256
+        self.buf = symm.empty((2 * half,), dtype=torch.uint8, device=device)
+        self.buf.zero_()
         self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
-        self.corners = self.buf[:cbytes].view(torch.float32).view(total, n_corners, 3)
-        self.status = self.buf[cbytes:].view(torch.int32)
+        self._views = []
+        for k in range(2):
+            b = self.buf[k * half:(k + 1) * half]
+            self._views.append((b[:cbytes].view(torch.float32).view(total, n_corners, 3),
+                                b[cbytes:cbytes + total * 4].view(torch.int32)))
         mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if use_multicast else 0
         if mc:
-            self.mode = "nvls multicast store"
-            cptrs, sptrs = [mc], [mc + cbytes]
+            self.mode, self._kind = "nvls multicast, multimem.st", 1
+            self._targets = [([mc + k * half], [mc + k * half + cbytes]) for k in range(2)]
         else:
-            self.mode = "peer stores"
-            cptrs = [int(p) for p in self.hdl.buffer_ptrs]
-            sptrs = [p + cbytes for p in cptrs]
-        extractor.set_gather_targets(cptrs, sptrs, rank * frames_local)
-        self._extractor = extractor
+            self.mode, self._kind = "peer stores", 0
+            bases = [int(p) for p in self.hdl.buffer_ptrs]
+            self._targets = [([p + k * half for p in bases], [p + k * half + cbytes for p in bases]) for k in range(2)]
+        self._extractor, self._slot, self._half = extractor, rank * frames_local, 0
+        self.corners, self.status = self._views[0]
+        self._point(0)
         self.hdl.barrier(channel=0)
 
+    def _point(self, k: int):
+        c, s = self._targets[k]
+        self._extractor.set_gather_targets(c, s, self._slot, self._kind)
+
     def barrier(self):
-        """All ranks' stores of this step are visible in every rank's buffer afterwards (runs on the current stream)."""
+        """All ranks' stores of this step are visible in every rank's buffer afterwards (runs on the current stream);
+        the next step's stores go to the other half."""
         self.hdl.barrier(channel=0)
+        self.corners, self.status = self._views[self._half]
+        self._half ^= 1
+        self._point(self._half)
 
     def close(self):
         self._extractor.set_gather_targets([], [], 0)

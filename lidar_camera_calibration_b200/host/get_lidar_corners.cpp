@@ -162,7 +162,8 @@ bool first_cloud(const std::string& path, const std::string& topic, ilcc2::Point
 
 int main(int argc, char** argv) {
   std::map<std::string, std::string> a = {{"--topic", "/velodyne_points"}, {"--camera", "front"}, {"--bag-num", "1"},
-                                          {"--device", "0"},               {"--out-dir", "."}};
+                                          {"--device", "0"},               {"--out-dir", "."},
+                                          {"--online", "0"}};
   for (int i = 1; i + 1 < argc; i += 2) a[argv[i]] = argv[i + 1];
   if (!a.count("--bag-prefix") || !a.count("--yaml") || !a.count("--clicks")) {
     std::cerr << "usage: get_lidar_corners --bag-prefix P --bag-num N --yaml Y --camera C --clicks F --out-dir D\n";
@@ -196,6 +197,14 @@ int main(int argc, char** argv) {
     ilcc2::PointCloud cloud;
     if (!first_cloud(bag_path, a["--topic"], cloud)) {
       std::cerr << "can't read lidar topic in " << bag_path << std::endl;  // get_lidar_corners.cpp:157-161
+      continue;
+    }
+    if (a["--online"] != "0") {  // lidar_chessboard_online.cpp:91-99: the plane of the clicked cluster, no corner fit
+      ilcc2::myPointCloud::Ptr board;
+      const bool found = est.get_chessboard_by_point(cloud.makeShared(), board, click);
+      std::cout << bag_idx << ": online found " << (found ? 1 : 0) << " plane " << board->size() << " click_in_cluster "
+                << est.online_diag().click_in_cluster << std::endl;
+      ++written;
       continue;
     }
     est.setROI(cloud.makeShared(), click);

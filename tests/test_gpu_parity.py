@@ -380,6 +380,62 @@ def test_hdl64_batch_parity_with_the_oracle(api, oracle):
     assert rep["hyp_equal_frac"] == 1.0, rep
 
 
+def test_sized_handle_same_results_and_capacity_status(api):
+    """ilcc2_create_sized: ROI-sized scratch of 8192 entries per frame instead of 28800 gives bit-identical results; a
+    capacity below a frame's ROI size is reported per frame (ILCC2_ROI_CAPACITY), nothing is truncated; a pool of two
+    global-memory clustering tables serves two frames whose ROI exceeds the shared-memory tables, the third reports
+    the same status."""
+    from lidar_camera_calibration_b200 import synth
+    F = 24
+    pts, clicks = synth.make_batch(F, start=300)
+    st0, c0, d0 = api.CornerExtractor(F, synth.VLP16.n_points).extract(pts, clicks, want_diag=True)
+    st1, c1 = api.CornerExtractor(F, synth.VLP16.n_points, roi_capacity=8192).extract(pts, clicks)
+    assert np.array_equal(st0, st1) and np.array_equal(c0, c1, equal_nan=True)
+    n_roi = np.array([d["n_roi"] for d in d0])
+    cap = int(np.sort(n_roi)[F // 2])                       # half of the frames fit
+    st2, c2, d2 = api.CornerExtractor(F, synth.VLP16.n_points, roi_capacity=cap).extract(pts, clicks, want_diag=True)
+    over = n_roi > cap
+    assert over.any() and (~over).any()
+    assert (st2[over] == 7).all() and np.isnan(c2[over]).all()
+    assert np.array_equal(st2[~over], st0[~over]) and np.array_equal(c2[~over], c0[~over], equal_nan=True)
+    assert np.array_equal(np.array([d["n_roi"] for d in d2]), n_roi)  # the true ROI size is still reported
+    big = np.flatnonzero(n_roi > 4096)                     # frames that need the global-memory tables
+    if big.size >= 3:
+        sel = big[:3]
+        st3, c3 = api.CornerExtractor(3, synth.VLP16.n_points, overflow_frames=2).extract(pts[sel], clicks[sel])
+        assert (st3 == 7).sum() == 1 and (st3 == st0[sel]).sum() == 2
+
+
+def test_online_variant_through_the_cpp_adaptor(api, oracle, bag_clouds, fixtures, tmp_path):
+    """LidarCornersEst::get_chessboard_by_point (LidarCornersEst.cpp:72-115; caller lidar_chessboard_online.cpp:91-99)
+    on the adaptor: the whole cloud is clustered at tolerance 0.10, the plane of the clicked cluster comes back, and the
+    call is false when that plane has < 500 points or the click's neighbour lies in no kept cluster (find_board)."""
+    import os
+    import subprocess
+    from lidar_camera_calibration_b200 import rosbag_lite as rb
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tool = os.path.join(root, "lidar_camera_calibration_b200", "host", "get_lidar_corners")
+    (tmp_path / "pointgrey.yaml").write_text(fixtures["yaml_text"])
+    p_o = oracle.default_params(roi_half_x=25.0, roi_half_y=25.0, roi_half_z=25.0, cluster_tolerance=0.1, min_board_points=500)
+    lines, want = [], []
+    for i, b in enumerate((1, 2, 3)):
+        rb.write_pointcloud2_bag(str(tmp_path / f"bag-{i + 1}.bag"), bag_clouds[b])
+        c = np.asarray(fixtures["lidar_corners"][str(b)]).mean(0)
+        if i == 2:
+            c = c + np.array([0.0, 0.0, 12.0])              # a click far above everything: its neighbour is in no kept cluster
+        lines.append(f"{c[0]:.6f} {c[1]:.6f} {c[2]:.6f}")
+        st, _, d = oracle.extract_frame(bag_clouds[b], c, flags=oracle.FLAG_AUTO, params=p_o)
+        want.append((int(st in (0, 4, 5) and d["n_board"] >= 500 and d["click_in_cluster"] == 1), d["n_board"], d["click_in_cluster"]))
+    (tmp_path / "clicks.txt").write_text("\n".join(lines) + "\n")
+    r = subprocess.run([tool, "--bag-prefix", str(tmp_path / "bag-"), "--bag-num", "3", "--yaml", str(tmp_path / "pointgrey.yaml"),
+                        "--camera", "pointgrey", "--clicks", str(tmp_path / "clicks.txt"), "--online", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = [tuple(int(t) for t in (ln.split()[3], ln.split()[5], ln.split()[7])) for ln in r.stdout.strip().splitlines()]
+    assert got == want, (got, want)
+    assert want[0][0] == 1 and want[1][0] == 1
+
+
 def test_sparse_roi_overflows_the_shared_memory_cell_table(api, oracle):
     """K2 keeps 4096 hash slots in shared memory; a ROI whose points occupy more than 3072 cells (a sparse cloud: most
     points alone in their cell) is handed over to the global-memory tables.  Clusters must not depend on the path."""
