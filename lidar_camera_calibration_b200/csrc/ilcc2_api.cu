@@ -395,7 +395,7 @@ int ilcc2_create_sized(const ilcc2_params* params, int device, int max_frames, i
   h->slot_frames = std::min(max_frames, h->e2e_chunk_frames);
   h->slot_bytes = (size_t)h->slot_frames * (size_t)max_points_per_frame * 32;
   for (int i = 0; i < ilcc2_handle::kDevSlots && ce == cudaSuccess; ++i) {
-    if ((size_t)i * h->slot_frames < (size_t)max_frames || i == 0) {
+    if (i == 0 || max_frames > h->slot_frames) {  // batches beyond one slot stream through all of them
       void* q = nullptr;
       A(cudaMalloc(&q, h->slot_bytes));
       h->d_stage[i] = static_cast<unsigned char*>(q);
