@@ -4,20 +4,24 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank per GPU)
     python bench.py --impl reference ...                     (the CPU path on the box's host cores)
 
-A "step" is one pass of the whole hot path (K1 roi_filter .. K5 board_fit, + the exchange of the corners between ranks
-when N>1: fused into K5 + one barrier, or an NCCL all-gather) over one batch of --frames synthetic VLP-16 frames per
-GPU (BASELINE.json configs[2]; 8 ranks x 1024
-frames = configs[4]).  Prints ONE JSON line (rank 0).
-  value        frames/s with the batch already resident in HBM (CUDA events around exactly K steps, max over ranks)
-  e2e          same metric through the C ABI with HOST buffers: pinned H2D of the batch + D2H of corners/status
-               inside the timed region
-  roofline     dominant kernel of the step vs the measured HBM peak (algorithmic bytes = SURVEY.md 8(d))
-  cpu_baseline the CPU oracle (a restatement; the reference needs ROS/PCL/Ceres and cannot be built here) timed
-               on a bounded sample in the same run
+A "step" is one pass of the whole hot path (K1 roi_filter, K2 cluster, K3+K4 plane_pca, K5 board_fit, + the exchange of
+the corners between ranks when N>1: fused into K5 + one barrier, or an NCCL all-gather) over one batch of --frames
+synthetic VLP-16 frames per GPU (BASELINE.json configs[2]; 8 ranks x 1024 frames = configs[4]).  ONE JSON line (rank 0):
+  value            frames/s with the batch already resident in HBM (CUDA events around exactly K steps, max over ranks)
+  e2e              same metric through the C ABI with HOST buffers: pinned H2D of the batch + D2H of corners/status inside
+                   the timed region; e2e_legs repeats it for pageable memory and for 32-byte PointCloud2 records
+  roofline         dominant kernel of the step vs the measured HBM peak (algorithmic bytes = SURVEY.md 8(d));
+                   roofline_compute: the issue-slot / fp64-pipe ceilings of the two latency-bound kernels (from the
+                   committed ncu capture)
+  parity           the step's batch compared frame for frame with the CPU oracle (outside the timed region)
+  hdl64, single_frame_latency_ms, accuracy_vs_truth_m   BASELINE.json configs[3], [0]/[1]
+  cpu_baseline     the CPU oracle (a restatement; the reference needs ROS/PCL/Ceres and cannot be built here) timed on
+                   a bounded sample in the same run: -O3 -march=native build and the parity build
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -34,6 +38,7 @@ if ROOT not in sys.path:
 METRIC = "lidar_frames_per_sec_16x1800_xyzi"
 UNIT = "frames/s"
 BYTES_PER_FRAME = 28800 * 16 + 12 + 35 * 12 + 4  # 461,236 B algorithmic bytes per VLP-16 frame
+BYTES_PER_FRAME_HDL64 = 131072 * 16 + 12 + 63 * 12 + 4
 HBM_FALLBACK_GBS = 6650.0                        # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -44,18 +49,37 @@ def hbm_peak():
         return HBM_FALLBACK_GBS, "fallback"
 
 
+def newest_profile(pattern: str):
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)))
+    return paths[-1] if paths else None
+
+
 def ncu_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel, from the newest committed
     `ncu --set full` capture of this workload (1024 frames): profiles/ncu_traffic_*.json, written by
-    tools/ncu_summary.py next to the text summaries. Returns {stage: bytes}."""
-    import glob
-    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_traffic_*.json")))
-    if not paths:
-        return {}
+    tools/ncu_summary.py next to the text summaries. Returns ({stage: bytes}, file name)."""
+    p = newest_profile("ncu_traffic_*.json")
+    if not p:
+        return {}, None
     try:
-        return {k: v["dram_bytes"] for k, v in json.load(open(paths[-1])).items()}
+        return {k: v["dram_bytes"] for k, v in json.load(open(p)).items()}, os.path.basename(p)
     except Exception:
-        return {}
+        return {}, None
+
+
+def ncu_compute_ceilings():
+    """roofline_compute: for the kernels that are NOT bandwidth-bound (K5 board_fit, K2 cluster) the ceilings they
+    can be measured against: issue slots (warp instructions / (SMs x 4 schedulers x elapsed cycles)) and the fp64 pipe.
+    Read from the newest committed ncu capture (profiles/ncu_compute_*.json, written by tools/ncu_summary.py)."""
+    p = newest_profile("ncu_compute_*.json")
+    if not p:
+        return None
+    try:
+        d = json.load(open(p))
+        d["source"] = "profiles/" + os.path.basename(p)
+        return d
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -68,6 +92,7 @@ class ClockSampler:
         self.gpu = gpu_index
         self.lines = []
         self.proc = None
+        self.marks = []
 
     def start(self):
         try:
@@ -79,16 +104,22 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        self.marks.append(time.time())
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.1)
         self.proc.terminate()
+        t0, t1 = (self.marks[0], self.marks[-1]) if len(self.marks) >= 2 else (0.0, float("inf"))
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if not (t0 - 0.03 <= ts <= t1 + 0.03):
+                continue
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 8:
                 continue
@@ -101,7 +132,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "samples taken between the first and the last timed step (device-resident + end-to-end loops)"}
 
 
 def host_threads() -> int:
@@ -159,13 +191,26 @@ def pnp_leg(api, ldist, synth, torch, dev, rank, world, start, gt, corners_all, 
                     "method's accuracy on this synthetic scene, not a parity figure"}
 
 
-def cpu_baseline(pts, clicks, sample_frames: int, threads: int):
+def cpu_rate(pts, clicks, n: int, threads: int, fast: bool):
     from oracle import oracle as O
-    n = min(sample_frames, pts.shape[0])
+    n = min(n, pts.shape[0])
+    O.extract_batch(pts[:max(2, min(threads, n))], clicks[:max(2, min(threads, n))], flags=O.FLAG_AUTO, threads=threads, fast=fast)
     t = time.time()
-    st, _ = O.extract_batch(pts[:n], clicks[:n], flags=O.FLAG_AUTO, threads=threads)
-    dt = time.time() - t
-    return n / dt, n, int((st == 0).sum())
+    st, _ = O.extract_batch(pts[:n], clicks[:n], flags=O.FLAG_AUTO, threads=threads, fast=fast)
+    return n / (time.time() - t), n, int((st == 0).sum())
+
+
+def cpu_baseline_block(pts, clicks, sample_frames: int):
+    """The CPU path on this box's host cores, same run: all cores (OpenMP over frames) and one thread (what the
+    single-threaded reference does), for the -O3 -march=native build and for the parity build (-O2 -ffp-contract=off)."""
+    threads = host_threads()
+    v, n, ok = cpu_rate(pts, clicks, sample_frames, threads, True)
+    v1, n1, _ = cpu_rate(pts, clicks, max(8, sample_frames // 32), 1, True)
+    vp, _, _ = cpu_rate(pts, clicks, sample_frames, threads, False)
+    return {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {n} frames of the step's batch, OpenMP over frames ({ok} ok), -O3 -march=native build",
+            "single_thread_value": v1, "single_thread_sample": f"first {n1} frames",
+            "parity_build_value": vp, "parity_build": "-O2 -ffp-contract=off (the build the parity tests use)"}
 
 
 def workload_text(frames: int) -> str:
@@ -174,34 +219,78 @@ def workload_text(frames: int) -> str:
             "7x5 board @0.15 m, colour phase auto (2 hypotheses x 2 solver phases per frame)")
 
 
+def base_config(args, world):
+    return {"workload": workload_text(args.frames), "frames_per_gpu": args.frames, "frames_total": world * args.frames,
+            "seed": 20181203}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; the real thing cannot be built here) on all
-    host threads, same metric / config; each step is a bounded sample of the workload."""
+    host threads, same metric / config: every step is the whole batch of --frames frames."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle as O
     threads = host_threads()
-    sample = args.ref_sample_frames
-    pts, clicks, _ = make_workload(sample, 0)
-    for _ in range(args.warmup):
-        O.extract_batch(pts[: max(threads, 16)], clicks[: max(threads, 16)], flags=O.FLAG_AUTO, threads=threads)
+    F = args.frames
+    pts, clicks, _ = make_workload(F, 0)
+    for _ in range(max(1, min(args.warmup, 3))):
+        O.extract_batch(pts[:max(threads * 4, 64)], clicks[:max(threads * 4, 64)], flags=O.FLAG_AUTO, threads=threads, fast=True)
+    steps = max(1, min(args.steps, args.ref_max_steps))
     t = time.time()
-    for _ in range(args.steps):
-        O.extract_batch(pts, clicks, flags=O.FLAG_AUTO, threads=threads)
+    ok = 0
+    for _ in range(steps):
+        st, _ = O.extract_batch(pts, clicks, flags=O.FLAG_AUTO, threads=threads, fast=True)
+        ok = int((st == 0).sum())
     dt = time.time() - t
-    fps = args.steps * sample / dt
+    fps = steps * F / dt
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_text(args.frames), "frames_per_gpu": args.frames,
-                   "frames_total": args.gpus * args.frames, "seed": 20181203,
-                   "reference_step": f"{sample} frames of that workload per step (bounded sample)"},
+        "config": base_config(args, args.gpus),
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} frames x {args.steps} steps, OpenMP over frames"},
+                         "sample": f"{F} frames x {steps} steps (the whole batch per step; steps capped at --ref-max-steps "
+                                   f"so the arm ends within minutes), OpenMP over frames, -O3 -march=native build, {ok} frames ok"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def hdl64_leg(api, synth, torch, dev, peak, frames=256):
+    """BASELINE.json configs[3]: 64-ring x 2048-point clouds, 9x7 board (32 generated frames repeated to `frames`)."""
+    base = min(frames, 32)
+    pts, clicks = synth.make_batch(base, scene=synth.SCENE_HDL64)
+    reps = (frames + base - 1) // base
+    pts, clicks = np.tile(pts, (reps, 1, 1))[:frames], np.tile(clicks, (reps, 1))[:frames]
+    ex = api.CornerExtractor(frames, synth.HDL64.n_points, params=api.default_params(cells_x=8, cells_y=10),
+                             roi_capacity=32768)
+    dp, dc = torch.from_numpy(pts).to(dev), torch.from_numpy(clicks).to(dev)
+    for _ in range(2):
+        st, _ = ex.extract_torch(dp, dc, flags=api.FLAG_AUTO)
+    torch.cuda.synchronize(dev)
+    R = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(R):
+        ex.extract_torch(dp, dc, flags=api.FLAG_AUTO)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / R
+    ex.set_profiling(True)
+    acc = {}
+    for _ in range(3):
+        ex.extract_torch(dp, dc, flags=api.FLAG_AUTO)
+        for k, v in ex.stage_times().items():
+            acc[k] = acc.get(k, 0.0) + v / 3
+    ex.set_profiling(False)
+    k1_gbs = BYTES_PER_FRAME_HDL64 * frames / (acc["roi_filter"] * 1e-3) / 1e9
+    out = {"frames": frames, "points_per_frame": synth.HDL64.n_points, "board": "9x7 @0.15 m", "ms_per_step": ms,
+           "frames_per_s": frames / (ms * 1e-3), "kernel_ms_per_step": acc, "frames_ok": int((st == 0).sum().item()),
+           "k1_achieved_gbs": k1_gbs, "k1_frac_of_hbm_peak": k1_gbs / peak,
+           "path_achieved_gbs": BYTES_PER_FRAME_HDL64 * frames / (ms * 1e-3) / 1e9,
+           "note": "32 generated frames repeated; ROI 12-16 k points per frame -> K2 and K5 run on their large layouts"}
+    ex.close()
+    return out
 
 
 def main():
@@ -211,9 +300,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
-    ap.add_argument("--cpu-sample-frames", type=int, default=256)
-    ap.add_argument("--ref-sample-frames", type=int, default=256)
+    ap.add_argument("--cpu-sample-frames", type=int, default=1024)
+    ap.add_argument("--ref-max-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the hdl64 / single-frame / pnp / projection legs")
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
                     help="multi-GPU exchange: auto = fused into K5 (multicast if available, else peer stores), nccl = all_gather")
     ap.add_argument("--watchdog-s", type=int, default=900, help="dump all stacks and exit if the run exceeds this")
@@ -231,16 +321,17 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     F, N, K, W = args.frames, synth.VLP16.n_points, args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # before the warm-up, so that it is up when the timed region starts
 
     pts, clicks, gt, gen_s = make_workload(F, rank * F, want_truth=True)
-    ex = api.CornerExtractor(F, N, device=local)
+    ex = api.CornerExtractor(F, N, device=local, roi_capacity=8192)
     ncorn = ex.n_corners
     # device-resident inputs (value) and pinned host inputs (e2e)
     d_pts, d_clicks = torch.from_numpy(pts).to(dev), torch.from_numpy(clicks).to(dev)
     d_corners = torch.empty((F, ncorn, 3), dtype=torch.float32, device=dev)
     d_status = torch.empty((F,), dtype=torch.int32, device=dev)
-    g_corners = torch.empty((world * F, ncorn, 3), dtype=torch.float32, device=dev) if world > 1 else None
-    g_status = torch.empty((world * F,), dtype=torch.int32, device=dev) if world > 1 else None
     h_pts, h_clicks = torch.from_numpy(pts).pin_memory(), torch.from_numpy(clicks).pin_memory()
     h_corners = torch.empty((F, ncorn, 3), dtype=torch.float32).pin_memory()
     h_status = torch.empty((F,), dtype=torch.int32).pin_memory()
@@ -252,7 +343,6 @@ def main():
     if world > 1 and args.gather != "nccl":
         try:
             fused = ldist.FusedGather(ex, F, ncorn, rank, world, dev, use_multicast=(args.gather != "peer"))
-            g_corners, g_status = fused.corners, fused.status
         except Exception as e:  # noqa: BLE001
             if rank == 0:
                 print(f"[bench] fused gather unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
@@ -263,92 +353,139 @@ def main():
         if int(flag.item()) == 0 and fused is not None:
             fused.close()
             fused = None
-            g_corners = torch.empty((world * F, ncorn, 3), dtype=torch.float32, device=dev)
-            g_status = torch.empty((world * F,), dtype=torch.int32, device=dev)
+    g_corners = torch.empty((world * F, ncorn, 3), dtype=torch.float32, device=dev) if world > 1 and fused is None else None
+    g_status = torch.empty((world * F,), dtype=torch.int32, device=dev) if world > 1 and fused is None else None
 
-    def step_device():
-        ex.extract_torch(d_pts, d_clicks, d_corners, d_status, flags=api.FLAG_AUTO, stream=stream)
+    def gathered():
+        return (fused.corners, fused.status) if fused is not None else (g_corners, g_status)
+
+    def exchange():
         if fused is not None:
             fused.barrier()
         elif world > 1:
             ldist.allgather_corners(d_corners, d_status, world, g_corners, g_status)
+
+    def step_device():
+        ex.extract_torch(d_pts, d_clicks, d_corners, d_status, flags=api.FLAG_AUTO, stream=stream)
+        exchange()
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- device-resident throughput ----
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident throughput: exactly K steps, nothing else inside the timed region ----
     for _ in range(W):
         step_device()
     barrier()
-    ex.set_profiling(True)
-    stage_ms = {s: 0.0 for s in api.STAGES}
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ex.launch_count
+    sampler.mark()
     e0.record(stream)
     for _ in range(K):
         step_device()
-        for s, ms in ex.stage_times().items():  # per-kernel CUDA events on the same stream (syncs on the step's end)
-            stage_ms[s] += ms
     e1.record(stream)
     barrier()
-    elapsed_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    ex.set_profiling(False)
+    sampler.mark()
+    elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = ex.launch_count - launches0
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
     n_ok = int((d_status == 0).sum().item())
 
+    # ---- per-kernel times: a separate pass with the library's CUDA events around every stage (same stream) ----
+    ex.set_profiling(True)
+    stage_ms = {s: 0.0 for s in api.STAGES}
+    Kp = max(5, min(K, 20))
+    for _ in range(Kp):
+        ex.extract_torch(d_pts, d_clicks, d_corners, d_status, flags=api.FLAG_AUTO, stream=stream)
+        for s, ms in ex.stage_times().items():
+            stage_ms[s] += ms / Kp
+    ex.set_profiling(False)
+    exchange()  # keeps the ranks' double buffers in step
+
     # ---- end to end through the C ABI with host buffers (H2D + kernels + D2H every step) ----
-    def step_e2e():
-        ex.extract_raw(h_pts.data_ptr(), F, N, 4, h_clicks.data_ptr(), h_corners.data_ptr(), h_status.data_ptr(),
-                       api.MEM_HOST, api.FLAG_AUTO, stream.cuda_stream)
+    def e2e_run(points_t, width, steps):
+        def one():
+            ex.extract_raw(points_t.data_ptr(), F, N, width, h_clicks.data_ptr(), h_corners.data_ptr(), h_status.data_ptr(),
+                           api.MEM_HOST, api.FLAG_AUTO, stream.cuda_stream)
+            if fused is not None:
+                fused.barrier()
+            elif world > 1:  # the call left this step's corners in the pinned host buffers: upload them, then gather
+                d_corners.copy_(h_corners, non_blocking=True)
+                d_status.copy_(h_status, non_blocking=True)
+                ldist.allgather_corners(d_corners, d_status, world, g_corners, g_status)
+        for _ in range(2):
+            one()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(steps):
+            one()
+        f1.record(stream)
+        barrier()
+        return max_over_ranks(f0.elapsed_time(f1)) / steps
 
     Ke = max(3, min(K, 10))
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record(stream)
-    for _ in range(Ke):
-        step_e2e()
-        if fused is not None:
-            fused.barrier()
-        elif world > 1:
-            ldist.allgather_corners(d_corners, d_status, world, g_corners, g_status)
-    f1.record(stream)
-    barrier()
-    e2e_ms = f0.elapsed_time(f1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    sampler.mark()
+    e2e_ms = e2e_run(h_pts, 4, Ke)
+    sampler.mark()
     e2e_match = bool(np.array_equal(h_corners.numpy(), d_corners.cpu().numpy(), equal_nan=True))
+    clocks = sampler.stop() if rank == 0 else None
+    legs = {"packed16_pinned": {"ms_per_step": e2e_ms, "frames_per_s": world * F / (e2e_ms * 1e-3),
+                                "h2d_bytes_per_step": int(F * N * 16 + F * 12)}}
+    if not args.no_extras:
+        # the reference's real input form: the `data` vector of a sensor_msgs::PointCloud2 -- pageable memory, 32-byte
+        # records x@0 y@4 z@8 intensity@16 (get_lidar_corners.cpp:136-164) -- and packed records in pageable memory
+        rec32 = np.zeros((F, N, 8), np.float32)
+        rec32[:, :, 0:3] = pts[:, :, 0:3]
+        rec32[:, :, 4] = pts[:, :, 3]
+        for name, arr, width in (("packed16_pageable", torch.from_numpy(pts), 4),
+                                 ("stride32_pinned", torch.from_numpy(rec32).pin_memory(), 8),
+                                 ("stride32_pageable", torch.from_numpy(rec32), 8)):
+            ms = e2e_run(arr, width, max(3, Ke // 2))
+            legs[name] = {"ms_per_step": ms, "frames_per_s": world * F / (ms * 1e-3),
+                          "h2d_bytes_per_step": int(F * N * width * 4 + F * 12),
+                          "matches_device_path": bool(np.array_equal(h_corners.numpy(), d_corners.cpu().numpy(), equal_nan=True))}
+        legs["pageable_over_pinned"] = {"packed16": legs["packed16_pageable"]["ms_per_step"] / legs["packed16_pinned"]["ms_per_step"],
+                                        "stride32": legs["stride32_pageable"]["ms_per_step"] / legs["stride32_pinned"]["ms_per_step"]}
+        del rec32
 
-    # ---- configs[4]: the PnP that follows the all-gather (not part of the frames/s figure) ----
-    step_device()
-    torch.cuda.synchronize(dev)
+    # ---- the exchange delivers what a plain NCCL all-gather delivers, also when consecutive steps differ ----
     gather_ok = None
-    if world > 1:  # whichever exchange ran, every rank must hold what a plain NCCL all-gather delivers, bit for bit
-        ref_c, ref_s = ldist.allgather_corners(d_corners, d_status, world)
-        same = torch.equal(ref_s, g_status) and torch.equal(torch.nan_to_num(ref_c, nan=-1.0), torch.nan_to_num(g_corners, nan=-1.0))
+    if world > 1:
+        same = True
+        for shift in (0, 1, 2):  # three consecutive steps on different inputs (frames rolled by `shift`)
+            p, c = (d_pts, d_clicks) if shift == 0 else (torch.roll(d_pts, shift, 0), torch.roll(d_clicks, shift, 0))
+            ex.extract_torch(p, c, d_corners, d_status, flags=api.FLAG_AUTO, stream=stream)
+            exchange()
+            gc, gs = gathered()
+            ref_c, ref_s = ldist.allgather_corners(d_corners, d_status, world)
+            same = same and torch.equal(ref_s, gs) and torch.equal(torch.nan_to_num(ref_c, nan=-1.0), torch.nan_to_num(gc, nan=-1.0))
         t = torch.tensor([1 if same else 0], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
         gather_ok = bool(t.item())
-    pnp = pnp_leg(api, ldist, synth, torch, dev, rank, world, rank * F, gt,
-                  g_corners if world > 1 else d_corners, g_status if world > 1 else d_status)
+    # ---- configs[4]: the PnP that follows the all-gather (not part of the frames/s figure) ----
+    step_device()
+    torch.cuda.synchronize(dev)
+    pnp = None
+    if not args.no_extras:
+        gc, gs = gathered() if world > 1 else (d_corners, d_status)
+        pnp = pnp_leg(api, ldist, synth, torch, dev, rank, world, rank * F, gt, gc, gs)
+    if rank != 0:
+        torch.distributed.destroy_process_group()
+        return
 
+    peak, peak_kind = hbm_peak()
     # ---- projecting the batch's points through the extrinsic (spaceToPlane + colouring) ----
-    proj = None
-    if rank == 0:
+    proj = hdl = None
+    single_ms = None
+    if not args.no_extras:
         pj = api.PnpSolver(local)
         flat = d_pts.view(-1, 4)
         pix = torch.empty((flat.shape[0], 2), dtype=torch.int32, device=dev)
@@ -365,62 +502,113 @@ def main():
         pbytes = flat.shape[0] * (16 + 8 + 4)
         proj = {"points": int(flat.shape[0]), "ms": pms, "points_per_s": flat.shape[0] / (pms * 1e-3),
                 "algorithmic_bytes": pbytes, "achieved_gbs": pbytes / (pms * 1e-3) / 1e9,
-                "valid_points": int(rgbv[:, 3].sum().item()),
+                "frac_of_hbm_peak": pbytes / (pms * 1e-3) / 1e9 / peak, "valid_points": int(rgbv[:, 3].sum().item()),
                 "note": "ilcc2_project_points over the step's 1024 x 28800 points: 16 B in, 12 B out per point"}
+        del pix, rgbv
+        # configs[0]/[1]: one frame at a time (device-resident, 8 warps per solve): latency of a single call
+        ex1 = api.CornerExtractor(1, N, device=local, roi_capacity=8192)
+        c1, s1 = torch.empty((1, ncorn, 3), dtype=torch.float32, device=dev), torch.empty((1,), dtype=torch.int32, device=dev)
+        for _ in range(3):
+            ex1.extract_torch(d_pts[:1], d_clicks[:1], c1, s1, flags=api.FLAG_AUTO, stream=stream)
+        torch.cuda.synchronize(dev)
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record(stream)
+        for i in range(20):
+            ex1.extract_torch(d_pts[i:i + 1], d_clicks[i:i + 1], c1, s1, flags=api.FLAG_AUTO, stream=stream)
+        q1.record(stream)
+        torch.cuda.synchronize(dev)
+        single_ms = q0.elapsed_time(q1) / 20
+        ex1.close()
+        try:
+            hdl = hdl64_leg(api, synth, torch, dev, peak)
+        except Exception as e:  # noqa: BLE001
+            hdl = {"error": f"{type(e).__name__}: {e}"}
 
-    if rank != 0:
-        torch.distributed.destroy_process_group()
-        return
+    # ---- accuracy against the planted ground truth (configs[1]) and parity against the oracle (whole batch) ----
+    st_h, c_h, diags = ex.extract(pts, clicks, flags=api.FLAG_AUTO, want_diag=True)   # host path, diag records
+    okf = np.flatnonzero(st_h == 0)
+    acc = np.array([synth.corner_set_distance(c_h[f], gt[f]) for f in okf]) if okf.size else np.zeros(1)
+    accuracy = {"frames": int(okf.size), "median": float(np.median(acc)), "p95": float(np.percentile(acc, 95)),
+                "frac_within_1cm": float((acc < 1e-2).mean()),
+                "note": "max corner distance per frame to the planted corners (order-normalised): the METHOD's accuracy on "
+                        "this scene (the reference's optimiser settles one square off on a minority of frames), not parity"}
+    parity = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O
+        parity = O.parity_report(pts, clicks, st_h, c_h, diags, threads=host_threads())
+        parity["note"] = ("oracle (parity build) on ALL frames of the step's batch vs the C ABI's results; corners compared "
+                          "index for index, tolerance = north_star's 1e-3 m")
+        parity["host_path_equals_device_path"] = bool(np.array_equal(c_h, d_corners.cpu().numpy(), equal_nan=True))
+
     value = world * F * K / (elapsed_ms * 1e-3)
-    e2e_value = world * F * Ke / (e2e_ms * 1e-3)
-    peak, peak_kind = hbm_peak()
+    e2e_value = world * F / (e2e_ms * 1e-3)
     dom = max(stage_ms, key=stage_ms.get)
-    per_launch_ms = {s: stage_ms[s] / K for s in stage_ms}
     bytes_launch = BYTES_PER_FRAME * F
 
     def roof(ms):
         a = bytes_launch / (ms * 1e-3) / 1e9
         return {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak}
 
-    traffic = ncu_traffic() if F == 1024 else {}
-    roofline = dict(roof(per_launch_ms[dom]), traffic=traffic.get(dom), kernel=dom, peak_source=f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-                    algorithmic_bytes_per_launch=bytes_launch, kernel_ms_per_launch=per_launch_ms[dom],
+    traffic, traffic_src = ncu_traffic() if F == 1024 else ({}, None)
+    tkey = {"plane_pca": "plane_pca"}.get(dom, dom)
+    roofline = dict(roof(stage_ms[dom]), traffic=traffic.get(tkey), traffic_source=traffic_src, kernel=dom,
+                    peak_source=f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                    algorithmic_bytes_per_launch=bytes_launch, kernel_ms_per_launch=stage_ms[dom],
                     share_of_step=stage_ms[dom] / sum(stage_ms.values()))
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_text(F), "frames_per_gpu": F, "frames_total": world * F, "seed": synth.BASE_SEED,
-                   "l2": f"inputs {F * N * 16 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
-                   "collective": ("none" if world == 1 else
-                                  f"fused into K5 ({fused.mode} into symmetric memory) + one signal-pad barrier per step"
-                                  if fused is not None else "nccl all_gather of corners+status per step"),
-                   "frames_ok": n_ok, "gather_equals_nccl_all_gather": gather_ok},
+        "config": dict(base_config(args, world),
+                       l2=f"inputs {F * N * 16 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
+                       collective=("none" if world == 1 else
+                                   f"fused into K5 ({fused.mode} into double-buffered symmetric memory) + one signal-pad barrier per step"
+                                   if fused is not None else "nccl all_gather of corners+status per step"),
+                       frames_ok=n_ok, gather_equals_nccl_all_gather=gather_ok),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * N * 16 + F * 12),
-                "d2h_bytes_per_step": int(F * ncorn * 12 + F * 4), "steps": Ke, "ms_per_step": e2e_ms / Ke,
-                "api": "ilcc2_extract_corners(mem_kind=ILCC2_MEM_HOST), pinned host buffers",
+                "d2h_bytes_per_step": int(F * ncorn * 12 + F * 4), "steps": Ke, "ms_per_step": e2e_ms,
+                "api": "ilcc2_extract_corners(mem_kind=ILCC2_MEM_HOST), pinned host buffers, packed 16-byte records",
                 "matches_device_path": e2e_match},
+        "e2e_legs": legs,
         "gpu_launches": int(launches),
         "roofline": roofline,
-        "roofline_path": dict(roof(elapsed_ms / K), note="whole step, all five kernels"),
-        "roofline_k1": dict(roof(per_launch_ms["roi_filter"]), kernel="roi_filter", traffic=traffic.get("roi_filter"),
+        "roofline_path": dict(roof(elapsed_ms / K), note="whole step, all kernels"),
+        "roofline_k1": dict(roof(stage_ms["roi_filter"]), kernel="roi_filter", traffic=traffic.get("roi_filter"),
                             note="the only kernel that reads all input bytes"),
-        "kernel_ms_per_step": per_launch_ms,
+        "roofline_compute": ncu_compute_ceilings(),
+        "kernel_ms_per_step": stage_ms,
+        "kernel_ms_note": "CUDA events of the library around each stage, a separate pass of the same workload (the timed "
+                          "region of `value` holds nothing but the K steps)",
+        "parity": parity,
+        "accuracy_vs_truth_m": accuracy,
+        "single_frame_latency_ms": single_ms,
+        "hdl64": hdl,
         "pnp": pnp,
-        "projection": dict(proj, frac_of_hbm_peak=proj["achieved_gbs"] / peak) if proj else None,
+        "projection": proj,
+        "scratch_mb": round(ex_scratch_mb(F, 8192, ncorn), 1), "staging_ring_mb": round(staging_mb(F), 1),
         "workload_gen_s": gen_s,
     }
-    if not args.no_cpu_baseline and world == 1:
-        threads = host_threads()
-        v, n, ok = cpu_baseline(pts, clicks, args.cpu_sample_frames, threads)
-        v1, n1, _ = cpu_baseline(pts, clicks, max(8, args.cpu_sample_frames // 16), 1)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": f"first {n} frames of the step's batch, OpenMP over frames ({ok} ok)",
-                               "single_thread_value": v1, "single_thread_sample": f"first {n1} frames"}
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_block(pts, clicks, args.cpu_sample_frames)
     print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def ex_scratch_mb(F, roi_cap, ncorn):
+    """Device scratch of a handle sized with roi_capacity (ilcc2_create_sized), MB: ROI-sized arrays (41 B per entry),
+    the pool of global-memory clustering tables, diag records (the staging ring for host batches: staging_mb)."""
+    ts = 1
+    while ts < 2 * roi_cap:
+        ts <<= 1
+    pool = F if roi_cap > 4096 else max(min(F, 8), F // 8)
+    return (F * roi_cap * 41 + pool * (2 * ts + 3 * roi_cap) * 4 + F * (320 + ncorn * 12 + 64)) / 1e6
+
+
+def staging_mb(F):
+    """The handle's device staging ring for host batches: 4 slots of 64 frames of 32-byte records."""
+    return 4 * min(F, 64) * 28800 * 32 / 1e6
 
 
 if __name__ == "__main__":

@@ -4,6 +4,8 @@
 // every compute entry point fails loudly when CUDA is unavailable.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sched.h>
+#include <xmmintrin.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -54,8 +56,11 @@ class CopyPool {
     for (auto& t : th_) t.join();
   }
   int threads() const { return n_; }
-  void copy(void* dst, const void* src, size_t bytes) {
-    if (bytes < (size_t)(1 << 20) || n_ == 1) {
+  // repack = false: plain copy of `bytes` bytes.  repack = true: `bytes` counts 32-byte PointCloud2 / pcl::PointXYZI
+  // records in src (x, y, z @0/4/8, intensity @16); dst receives packed 16-byte (x, y, z, intensity) records, written
+  // with streaming stores -- the padding and the ring field never cross PCIe.
+  void copy(void* dst, const void* src, size_t bytes, bool repack = false) {
+    if (!repack && (bytes < (size_t)(1 << 20) || n_ == 1)) {
       memcpy(dst, src, bytes);
       return;
     }
@@ -64,6 +69,7 @@ class CopyPool {
       dst_ = static_cast<unsigned char*>(dst);
       src_ = static_cast<const unsigned char*>(src);
       bytes_ = bytes;
+      repack_ = repack;
       pending_ = n_;
       ++gen_;
     }
@@ -82,10 +88,24 @@ class CopyPool {
       if (stop_) return;
       unsigned char* d = dst_;
       const unsigned char* sp = src_;
+      const bool rp = repack_;
       const size_t per = ((bytes_ + n_ - 1) / n_ + 4095) & ~(size_t)4095, b = std::min(bytes_, per * i),
                    e = std::min(bytes_, per * (i + 1));
       l.unlock();
-      if (e > b) memcpy(d + b, sp + b, e - b);
+      if (e > b) {
+        if (!rp) {
+          memcpy(d + b, sp + b, e - b);
+        } else {
+          const float* in = reinterpret_cast<const float*>(sp + (b >> 5 << 5));
+          float* out = reinterpret_cast<float*>(d + (b >> 5 << 4));
+          for (size_t k = 0, n = (e >> 5) - (b >> 5); k < n; ++k, in += 8, out += 4) {
+            const __m128 a = _mm_loadu_ps(in);                               // x y z pad
+            const __m128 zi = _mm_shuffle_ps(a, _mm_load_ss(in + 4), _MM_SHUFFLE(0, 0, 2, 2));  // z z i i
+            _mm_stream_ps(out, _mm_shuffle_ps(a, zi, _MM_SHUFFLE(2, 0, 1, 0)));  // x y z i
+          }
+          _mm_sfence();
+        }
+      }
       l.lock();
       if (--pending_ == 0) done_.notify_one();
     }
@@ -99,6 +119,7 @@ class CopyPool {
   unsigned char* dst_ = nullptr;
   const unsigned char* src_ = nullptr;
   size_t bytes_ = 0;
+  bool repack_ = false;
   int pending_ = 0;
 };
 
@@ -154,7 +175,7 @@ struct ilcc2_handle {
   static constexpr int kWorkStreams = 4;   // chunks are computed round-robin on these, so their kernels overlap
   cudaStream_t work_stream[kWorkStreams] = {};
   cudaEvent_t ev_work_done[kWorkStreams] = {};
-  int e2e_chunk_frames = 128;
+  int e2e_chunk_frames = 64;
   int dev_chunks = 1;        // > 1 (ILCC2_DEV_CHUNKS): device-resident batches are cut into this many concurrent chunks
   bool ev_valid = false;
   int64_t launches = 0;
@@ -599,7 +620,7 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
   const bool multi = n_chunks > 1;
   // record offset (in point records) of a frame within the caller's buffer
   auto rec_off = [&](int f) -> long long { return frame_offsets ? (long long)frame_offsets[f] : (long long)f * points_per_frame; };
-  bool pageable = false;
+  bool pageable = false, repack = false;
   unsigned char* big = nullptr;
   if (host) {
     cudaPointerAttributes pa;
@@ -609,6 +630,8 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
     } else {
       pageable = pa.type == cudaMemoryTypeUnregistered;
     }
+    static const bool driver_staging = getenv("ILCC2_DRIVER_STAGING") != nullptr;  // A/B: let cudaMemcpyAsync stage pageable memory
+    if (driver_staging) pageable = false;
     if (!multi && bytes > h->slot_bytes) {
       // one chunk that does not fit a slot (profiling / debug runs of large host batches): a buffer grown on demand
       if (bytes > h->points_big_bytes) {
@@ -626,11 +649,23 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
         CU_TRY(h, cudaHostAlloc(&q, h->slot_bytes, cudaHostAllocDefault));
         h->h_stage[i] = static_cast<unsigned char*>(q);
       }
-      int nt = (int)std::thread::hardware_concurrency() / 2;
+      int nt = (int)std::thread::hardware_concurrency();
+      cpu_set_t set;
+      if (sched_getaffinity(0, sizeof(set), &set) == 0) nt = CPU_COUNT(&set);
+      nt = std::min(nt, 12);
       if (const char* e = getenv("ILCC2_STAGE_THREADS")) nt = atoi(e);
-      h->pool = new CopyPool(std::max(1, std::min(nt, 8)));
+      h->pool = new CopyPool(std::max(1, std::min(nt, 64)));
+    }
+    // 32-byte records in pageable memory are compacted to packed XYZI on their way through the page-locked ring (the
+    // host pass exists anyway): half the PCIe bytes, and K1 reads packed records.  Same floats, same results.
+    repack = pageable && multi && point_step == 32 && off_x == 0 && off_y == 4 && off_z == 8 && off_intensity == 16 &&
+             getenv("ILCC2_NO_REPACK") == nullptr;
+    if (repack) {
+      w.step = 16;
+      w.oi = 12;
     }
   }
+  const int dev_step = repack ? 16 : point_step;
   if (multi) {
     CU_TRY(h, cudaEventRecord(h->ev_start, s));  // everything queued on s so far (small copies, memsets) comes first
     if (host) CU_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_start, 0));
@@ -653,8 +688,8 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
       if (pageable && multi) {
         const int ps = c % ilcc2_handle::kPinSlots;
         if (h->pin_slot_used[ps]) CU_TRY(h, cudaEventSynchronize(h->ev_h2d_done[ps]));
-        h->pool->copy(h->h_stage[ps], src, cbytes);
-        CU_TRY(h, cudaMemcpyAsync(dst, h->h_stage[ps], cbytes, cudaMemcpyHostToDevice, xs));
+        h->pool->copy(h->h_stage[ps], src, cbytes, repack);
+        CU_TRY(h, cudaMemcpyAsync(dst, h->h_stage[ps], repack ? cbytes / 2 : cbytes, cudaMemcpyHostToDevice, xs));
         CU_TRY(h, cudaEventRecord(h->ev_h2d_done[ps], xs));
         h->pin_slot_used[ps] = true;
       } else {
@@ -664,7 +699,7 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
         CU_TRY(h, cudaEventRecord(h->ev_copied[c % ilcc2_handle::kMaxChunks], xs));
         CU_TRY(h, cudaStreamWaitEvent(cs, h->ev_copied[c % ilcc2_handle::kMaxChunks], 0));
       }
-      w.points = dst - (size_t)r0 * point_step;  // kernels index records by their offset within the whole batch
+      w.points = dst - (size_t)r0 * dev_step;  // kernels index records by their offset within the whole batch
     }
     launch_roi_filter(w, h->dp, cs);
     if (host && multi) {

@@ -109,7 +109,10 @@ static int run_rank(int rank, int world, const std::map<std::string, std::string
   CK(cudaStreamCreate(&s));
   std::vector<float> hc((size_t)N * ncorn * 3);
   std::vector<int32_t> hs(N);
-  if (rank == 0) printf("world %d frames %d fused %d\n", world, N, ilcc2_gather_is_fused(h));
+  if (rank == 0) {
+    printf("world %d frames %d fused %d\n", world, N, ilcc2_gather_is_fused(h));
+    fflush(stdout);
+  }
   for (int step = 0; step < K; ++step) {
     const int r = count ? step % count : 0;  // rotate the shard by r frames: frame i of this step = frame (i + r) % count
     const size_t fb = (size_t)P * 16;

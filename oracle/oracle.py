@@ -74,6 +74,34 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+_lib_fast = None
+
+
+def _cpu_tag() -> str:
+    """Short hash of this machine's CPU model + ISA flags: the -march=native build is only valid where it was made."""
+    import hashlib
+    try:
+        txt = open("/proc/cpuinfo").read()
+        keep = [ln for ln in txt.splitlines() if ln.startswith(("model name", "flags"))][:2]
+    except OSError:
+        keep = []
+    return hashlib.sha1("\n".join(keep).encode()).hexdigest()[:10]
+
+
+def lib_fast() -> C.CDLL:
+    """The -O3 -march=native CPU-baseline build (bench.py's cpu_baseline / --impl reference legs only), compiled on
+    first use on the machine that runs it.  Same entry points as lib(); never used as the parity checker."""
+    global _lib_fast
+    if _lib_fast is None:
+        name = f"libilcc2_oracle_fast_{_cpu_tag()}.so"
+        path = os.path.join(_HERE, name)
+        if not os.path.exists(path) or any(os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(path)
+                                           for f in ("ilcc2_oracle.c", "ilcc2_pnp_oracle.c", "ilcc2_oracle.h")):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "fast", f"FAST={name}"])
+        L = C.CDLL(path)
+        _declare(L)
+        _lib_fast = L
+    return _lib_fast
 
 
 def lib() -> C.CDLL:
@@ -81,6 +109,13 @@ def lib() -> C.CDLL:
     if _lib is None:
         build()
         L = C.CDLL(_LIB_PATH)
+        _declare(L)
+        _lib = L
+    return _lib
+
+
+def _declare(L) -> None:
+    if True:
         L.ilcc2o_default_params.argtypes = [C.POINTER(Params)]
         L.ilcc2o_extract_frame.restype = C.c_int
         L.ilcc2o_extract_frame.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -119,8 +154,6 @@ def lib() -> C.CDLL:
         L.ilcc2o_project_points.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double,
                                             C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
-        _lib = L
-    return _lib
 
 
 def default_params(**overrides) -> Params:
@@ -170,9 +203,10 @@ def extract_frame(points: np.ndarray, click, flags: int = 0, plane_index_delta: 
 
 
 def extract_batch(points: np.ndarray, clicks: np.ndarray, flags=FLAG_AUTO, params: Params | None = None,
-                  threads: int = 1, want_diag: bool = False):
-    """points: (F, N, 4|8) float32; clicks (F,3). Returns (status[F], corners[F,ncorn,3][, diags])."""
-    L = lib()
+                  threads: int = 1, want_diag: bool = False, fast: bool = False):
+    """points: (F, N, 4|8) float32; clicks (F,3). Returns (status[F], corners[F,ncorn,3][, diags]).
+    fast: the -O3 -march=native baseline build (timing only) instead of the parity build."""
+    L = lib_fast() if fast else lib()
     p = params or default_params()
     assert points.ndim == 3 and points.dtype == np.float32 and points.flags.c_contiguous
     F, N, w = points.shape

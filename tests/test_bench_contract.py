@@ -12,21 +12,22 @@ def test_reference_arm_prints_the_contract_line():
     env = dict(os.environ)
     env.pop("RANK", None)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1",
-                        "--warmup", "1", "--ref-sample-frames", "8"], capture_output=True, text=True, timeout=600, env=env)
+                        "--warmup", "1", "--frames", "16"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "lidar_frames_per_sec_16x1800_xyzi" and d["unit"] == "frames/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
-    assert d["config"]["workload"].startswith("1024 synthetic VLP-16 frames")
+    assert d["config"]["workload"].startswith("16 synthetic VLP-16 frames") and d["config"]["frames_per_gpu"] == 16
+    assert set(d["config"]) == {"workload", "frames_per_gpu", "frames_total", "seed"}   # the keys both arms share
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "8 frames" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "16 frames x 1 steps" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
 def test_reference_arm_is_silent_on_other_ranks():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
-                        "--warmup", "1", "--ref-sample-frames", "8"], capture_output=True, text=True, timeout=600, env=env)
+                        "--warmup", "1", "--frames", "16"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""

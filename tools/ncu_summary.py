@@ -35,14 +35,16 @@ WANT = [
 ]
 
 
-def main(rep, out=None, traffic_json=None):
+def main(rep, out=None, traffic_json=None, compute_json=None):
     """traffic_json: also write {kernel base name: {"dram_bytes": read+write, "time_us": ...}} for the longest launch
-    of every kernel (bench.py's roofline.traffic reads it)."""
+    of every kernel (bench.py's roofline.traffic reads it).  compute_json: the issue-slot / fp64-pipe ceilings of every
+    kernel (bench.py's roofline_compute): warp instructions / (SMs x 4 schedulers x elapsed cycles)."""
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     lines = []
     traffic = {}
+    compute = {}
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tmul = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "usecond": 1.0, "msecond": 1e3, "nsecond": 1e-3, "second": 1e6}
     for r in rows[2:]:
@@ -53,6 +55,26 @@ def main(rep, out=None, traffic_json=None):
         byt = float(r[i_r]) * mult.get(units[i_r], 1.0) + float(r[i_w]) * mult.get(units[i_w], 1.0)
         if base not in traffic or t_us > traffic[base]["time_us"]:
             traffic[base] = {"dram_bytes": byt, "time_us": t_us, "kernel": name[:80]}
+
+            def col(metric):
+                for i, hname in enumerate(hdr):
+                    if hname == metric:
+                        try:
+                            return float(r[i].replace(",", ""))
+                        except ValueError:
+                            return None
+                return None
+            inst, cyc = col("smsp__inst_executed.sum"), col("sm__cycles_elapsed.max")
+            if inst and cyc:
+                sms = 148
+                compute[base] = {
+                    "bound": "issue slots", "warp_instructions": inst, "elapsed_cycles": cyc, "sms": sms,
+                    "achieved": inst / cyc / (sms * 4), "peak": 1.0, "unit": "warp instructions / scheduler / cycle",
+                    "frac": inst / cyc / (sms * 4),
+                    "issue_active_pct_of_active_cycles": col("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                    "fp64_pipe_active_pct": col("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                    "warps_active_pct": col("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                    "registers_per_thread": col("launch__registers_per_thread"), "time_us": t_us, "kernel": name[:80]}
         lines.append(f"== {r[hdr.index('Kernel Name')][:70]}  grid {r[hdr.index('Grid Size')]} block {r[hdr.index('Block Size')]}")
         for w in WANT:
             for i, h in enumerate(hdr):
@@ -65,6 +87,9 @@ def main(rep, out=None, traffic_json=None):
     if traffic_json:
         import json
         json.dump(traffic, open(traffic_json, "w"), indent=1)
+    if compute_json:
+        import json
+        json.dump(compute, open(compute_json, "w"), indent=1)
 
 
 if __name__ == "__main__":
