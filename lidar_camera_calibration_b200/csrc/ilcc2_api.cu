@@ -379,12 +379,11 @@ int ilcc2_create_sized(const ilcc2_params* params, int device, int max_frames, i
   A(dev_alloc(h, &w.fit_order, F));
   A(dev_alloc(h, &w.fit_done, F));
   w.num_sms = prop.multiProcessorCount;
-  w.fit_stride = (h->cap + 31) / 32 + 2ll * kFitGlobalTeam * h->cap;
   bool big_layout = h->max_points > kFitBigFrame;
   if (const char* e = getenv("ILCC2_FIT_LAYOUT")) big_layout = std::string(e) == "big";  // tests: force either K5 layout
   w.fit_bits_cap = big_layout ? kFitBitsCapBig : kFitBitsCap;
   w.fit_team_cap = big_layout ? kFitTeamCapBig : kFitTeamCap;
-  A(dev_alloc(h, &w.fit_scratch, h->cap > w.fit_bits_cap ? F * (size_t)w.fit_stride : 1));
+  A(dev_alloc(h, &w.fit_pool_next, 1));
   A(dev_alloc(h, &h->d_clicks, F * 3));
   A(dev_alloc(h, &h->d_flags, F));
   A(dev_alloc(h, &h->d_pdelta, F));
@@ -436,6 +435,8 @@ int ilcc2_create_sized(const ilcc2_params* params, int device, int max_frames, i
   }
   w.rnd_table = h->d_rnd;
   w.cap = h->cap;
+  w.fit_scratch = reinterpret_cast<uint32_t*>(w.cl_scratch);  // K5's global tables reuse the pool K2 has finished with
+  w.fit_stride = w.cl_stride;
   *out = h;
   return ILCC2_SUCCESS;
 }
@@ -549,6 +550,7 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
   w.diag = h->d_diag;
   CU_TRY(h, cudaMemsetAsync(h->d_diag, 0, sizeof(ilcc2_diag) * n_frames, s));
   CU_TRY(h, cudaMemsetAsync(w.cl_pool_next, 0, sizeof(int), s));
+  CU_TRY(h, cudaMemsetAsync(w.fit_pool_next, 0, sizeof(int), s));
 
   const bool prof = h->profiling;
   static const bool debug_sync = getenv("ILCC2_DEBUG_SYNC") != nullptr;  // debugging aid: sync + report per stage

@@ -44,18 +44,19 @@ constexpr int kPlaneThreads = 128;    // K3/K4 CTA size == canonical reduction w
 constexpr int kFitMaxTeam = 8;
 constexpr int kFitGlobalTeam = 2;     // team size of the global-memory instantiation (frames above kFitBitsCap points)
 #ifndef FIT_TEAM_CAP
-#define FIT_TEAM_CAP 3328
+#define FIT_TEAM_CAP 4096
 #endif
-// K5: points per chunk of a solve (multiple of 32 * kFitMaxTeam).  Each of the T warps of a team owns a candidate list of
-// kFitTeamCap / T 16-bit entries in shared memory, so the footprint (6.5 KB + 1 KB of colour bits per CTA) does not
-// depend on T and most of the SM's 256 KB stay L1 for the points.  Frames with more points are evaluated in chunks.
+// K5: optimiser points of a frame that the shared-memory instantiation takes (multiple of 32 * kFitMaxTeam).  Each of
+// the T warps of a team owns a candidate list of kFitTeamCap / T 16-bit entries in shared memory, so the footprint
+// (2 x 8 KB of lists + 0.5 KB of colour bits per CTA) does not depend on T and most of the SM's 256 KB stay L1 for the
+// points.  Frames with more points take the global-memory instantiation (tables from the handle's overflow pool).
 constexpr int kFitTeamCap = FIT_TEAM_CAP;
-constexpr int kFitBitsCap = 8192;      // K5: colour bits kept in shared memory; larger frames take the global-memory path
+constexpr int kFitBitsCap = kFitTeamCap;
 // Handles created for big frames (max_points_per_frame > kFitBigFrame, e.g. the 64 x 2048 HDL-64-like clouds whose
-// boards hold 10-14 k optimiser points) use a larger shared-memory layout instead: 4 KB of colour bits + 32 KB of lists.
+// boards hold 10-14 k optimiser points) use a larger shared-memory layout instead: 2 KB of colour bits + 2 x 32 KB of lists.
 constexpr int kFitBigFrame = 65536;
 constexpr int kFitTeamCapBig = 16384;
-constexpr int kFitBitsCapBig = 32768;
+constexpr int kFitBitsCapBig = kFitTeamCapBig;
 #ifndef FIT_BATCH
 #define FIT_BATCH 8
 #endif
@@ -104,8 +105,9 @@ struct Workspace {
   int fit_bits_cap;            // K5 shared-memory layout of this handle: colour-bit capacity (points) ...
   int fit_team_cap;            // ... and points per chunk of a solve (list entries per team)
   int num_sms;
-  uint32_t* fit_scratch;       // [F][fit_stride] K5 global-memory path: colour bits + two index lists
-  long long fit_stride;
+  uint32_t* fit_scratch;       // K5 global-memory path: colour bits + index lists, in slots of the SAME pool as
+  long long fit_stride;        // cl_scratch (K2 is done with it by then): slot stride = cl_stride, taken through
+  int* fit_pool_next;          // fit_pool_next
   const uint32_t* rnd_table;   // [kRndTable] PCL RANSAC draws
   // outputs (device)
   float* corners;              // [F][ncorners][3]

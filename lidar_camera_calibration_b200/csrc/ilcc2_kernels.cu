@@ -1318,6 +1318,9 @@ void launch_plane_pca(const Workspace& w, const DevParams& p, cudaStream_t s) {
 #ifndef FIT_PAIR
 #define FIT_PAIR 1
 #endif
+#if !FIT_PAIR
+#error "FIT_PAIR = 0 (one CTA per hypothesis, round 1) is no longer maintained: the overflow-pool slots are per frame"
+#endif
 struct VbModel {
   int tlw;
   double Wd, Hd, g, inv_g, wg2, hg2, ha, hb, two_ha;
@@ -1626,25 +1629,46 @@ template <typename IdxT, bool JAC>
 __device__ __forceinline__ void list_pass(const float2* __restrict__ yz, const uint32_t* __restrict__ wbits,
                                           const IdxT* list, int list_cap, const VbModel& M, bool oob, double c, double s,
                                           double w0, double ty, double tz, int lane, int n1, int n2, double (&a)[9]) {
-  // L1: colour mismatch or not certain -> full residual.  Software pipeline: index, point and colour bit of the next
-  // iteration are fetched (shared-memory list -> L1 gather, a dependent chain) while this one is evaluated.
-  int kn = lane < n1 ? (int)list[lane] : 0;
-  float2 qn = __ldg(yz + kn);
-  unsigned wn = wbits[kn >> 5];
-  for (int e0 = 0; e0 < n1; e0 += 32) {
-    const bool act = e0 + lane < n1;
-    const int k = kn;
-    const float2 q = qn;
-    const unsigned wx = ((wn >> (k & 31)) & 1u) ^ (unsigned)M.tlw;
-    const int en = e0 + 32 + lane;
-    kn = en < n1 ? (int)list[en] : 0;
-    qn = __ldg(yz + kn);
-    wn = wbits[kn >> 5];
-    const double y = (double)q.x, z = (double)q.y;
-    double si, sj;
-    double r = vb_eval<JAC>(M, oob, y, z, wx, c, s, w0, ty, tz, si, sj);
-    if (!act) r = 0.0;
-    accumulate_point(M, JAC, y, z, c, s, r, si, sj, a);
+  // L1: colour mismatch or not certain -> full residual.  LIST_U points per lane and iteration: their residual chains
+  // (~50 dependent fp64 operations each) are independent, the sums are still taken in list order.  Software pipeline:
+  // index, point and colour bit of the next iteration are fetched (shared-memory list -> L1 gather, a dependent chain)
+  // while this one is evaluated.
+#ifndef LIST_U
+#define LIST_U 1
+#endif
+  constexpr int LU = LIST_U;
+  int kn[LU];
+  float2 qn[LU];
+  unsigned wn[LU];
+#pragma unroll
+  for (int u = 0; u < LU; ++u) {
+    const int en = 32 * u + lane;
+    kn[u] = en < n1 ? (int)list[en] : 0;
+    qn[u] = __ldg(yz + kn[u]);
+    wn[u] = wbits[kn[u] >> 5];
+  }
+  for (int e0 = 0; e0 < n1; e0 += 32 * LU) {
+    bool act[LU];
+    double y[LU], z[LU], r[LU], si[LU], sj[LU];
+    unsigned wx[LU];
+#pragma unroll
+    for (int u = 0; u < LU; ++u) {
+      act[u] = e0 + 32 * u + lane < n1;
+      y[u] = (double)qn[u].x;
+      z[u] = (double)qn[u].y;
+      wx[u] = ((wn[u] >> (kn[u] & 31)) & 1u) ^ (unsigned)M.tlw;
+      const int en = e0 + 32 * (LU + u) + lane;
+      kn[u] = en < n1 ? (int)list[en] : 0;
+      qn[u] = __ldg(yz + kn[u]);
+      wn[u] = wbits[kn[u] >> 5];
+    }
+#pragma unroll
+    for (int u = 0; u < LU; ++u) r[u] = vb_eval<JAC>(M, oob, y[u], z[u], wx[u], c, s, w0, ty, tz, si[u], sj[u]);
+#pragma unroll
+    for (int u = 0; u < LU; ++u) {
+      if (!act[u]) r[u] = 0.0;
+      accumulate_point(M, JAC, y[u], z[u], c, s, r[u], si[u], sj[u], a);
+    }
   }
   if (oob) {
     for (int e0 = 0; e0 < n2; e0 += 32) {  // L2: certainly outside the board -> distance to the nearest edges
@@ -1973,7 +1997,6 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
   const bool oob = oob_i != 0;
   const int wt = (threadIdx.x >> 5) % T, team = (threadIdx.x >> 5) / T;  // warp of the team; team of the CTA
   int parity = *parity_io;
-  const int team_cap = Fp->team_cap;  // points per chunk: each warp of the team classifies / evaluates its share
 
   ScalarWs& ws = *ws_shared;
   double *xc = ws.xc, *cand = ws.cand, *g = ws.g, *H = ws.H, *scale = ws.scale, *xbest = ws.xbest;
@@ -2018,19 +2041,17 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
 #pragma unroll
     for (int q = 0; q < 9; ++q) a[q] = 0.0;
     int n1 = 0, n2 = 0;
-    for (int k0 = 0; k0 < n; k0 += team_cap) {
+    {
 #ifdef FIT_TIMING
       const long long tc0 = clock64();
 #endif
-      // this warp's share of the chunk: every T-th group of 32 * CLS_UNROLL points
-      const int k1 = min(k0 + team_cap, n);
-      classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, cand[1], cand[2], lane, k0 + wt * (32 * CLS_UNROLL), k1,
+      // this warp's share of the frame's points: every T-th group of 32 * CLS_UNROLL points
+      classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, cand[1], cand[2], lane, wt * (32 * CLS_UNROLL), n,
                           T * 32 * CLS_UNROLL, n1, n2);
 #ifdef FIT_TIMING
       t_cls += clock64() - tc0;
 #endif
       list_pass<IdxT, false>(yz, wbits, list, list_cap, M, oob, cs, sn, w0, cand[1], cand[2], lane, n1, n2, a);
-      if (k0 + team_cap < n) __syncwarp();
     }
     double cc1[1] = {warp_butterfly(a[0])};
     team_sum<1, T>(cc1, slots, wt, lane, parity, team);
@@ -2051,23 +2072,13 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
       accept = quality > 1e-3;
     }
     if (accept) {
-      // ---- Jacobian at the accepted point: reuse the lists when the frame is a single chunk ----
+      // ---- Jacobian at the accepted point: from the lists of the evaluation that has just been accepted ----
       for (int i = 0; i < 3; ++i) xc[i] = cand[i];
       xnorm = norm3(xc);
       x_cost = cc;
 #pragma unroll
       for (int q = 0; q < 9; ++q) a[q] = 0.0;
-      if (n <= team_cap) {
-        list_pass<IdxT, true>(yz, wbits, list, list_cap, M, oob, cs, sn, w0, xc[1], xc[2], lane, n1, n2, a);
-      } else {
-        for (int k0 = 0; k0 < n; k0 += team_cap) {
-          __syncwarp();
-          const int k1 = min(k0 + team_cap, n);
-          classify_pass<IdxT>(yz, wbits, list, list_cap, M, oob, cs, sn, xc[1], xc[2], lane, k0 + wt * (32 * CLS_UNROLL), k1,
-                              T * 32 * CLS_UNROLL, n1, n2);
-          list_pass<IdxT, true>(yz, wbits, list, list_cap, M, oob, cs, sn, w0, xc[1], xc[2], lane, n1, n2, a);
-        }
-      }
+      list_pass<IdxT, true>(yz, wbits, list, list_cap, M, oob, cs, sn, w0, xc[1], xc[2], lane, n1, n2, a);
 #pragma unroll
       for (int q = 0; q < 9; ++q) a[q] = warp_butterfly(a[q]);
       team_sum<9, T>(a, slots, wt, lane, parity, team);
@@ -2351,7 +2362,21 @@ __global__ void __launch_bounds__(32 * T * (FIT_PAIR ? 2 : 1), (SMEM ? FIT_WARPS
     F.yz = gyz;
     wbits = reinterpret_cast<uint32_t*>(fit_sm);
   } else {
-    uint32_t* g = w.fit_scratch + (size_t)f * w.fit_stride;
+    if (tid == 0) s_last = atomicAdd(w.fit_pool_next, 1);  // next free slot of the overflow pool
+    __syncthreads();
+    if (s_last >= w.cl_pool_slots) {  // more frames beyond the shared-memory layout than the handle holds tables for
+      for (int i = tid; i < p.ncorners * 3; i += kThreads) {
+        corners[i] = NAN;
+        gather_store_corner(w, f, p.ncorners, i, NAN);
+      }
+      if (tid == 0) {
+        d->status = ILCC2_ROI_CAPACITY;
+        w.status[f] = ILCC2_ROI_CAPACITY;
+        gather_store_status(w, f, ILCC2_ROI_CAPACITY);
+      }
+      return;
+    }
+    uint32_t* g = w.fit_scratch + (size_t)s_last * w.fit_stride;
     wbits = g;
     F.yz = gyz;
     F.bits_bytes = 0;
