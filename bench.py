@@ -306,6 +306,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the hdl64 / single-frame / pnp / projection legs")
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
                     help="multi-GPU exchange: auto = fused into K5 (multicast if available, else peer stores), nccl = all_gather")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin ranks to the NUMA node of their GPU")
     ap.add_argument("--watchdog-s", type=int, default=900, help="dump all stacks and exit if the run exceeds this")
     args = ap.parse_args()
     import faulthandler
@@ -320,6 +321,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one rank per GPU: keep this rank's threads and page-locked buffers on the NUMA node of its GPU (H2D copies of the
+    # end-to-end legs then stay off the inter-socket link); a single rank keeps all cores (cpu_baseline uses them)
+    numa = ldist.bind_to_gpu_numa(local) if world > 1 and not args.no_numa_bind else None
     F, N, K, W = args.frames, synth.VLP16.n_points, args.steps, max(args.warmup, 3)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -564,7 +568,7 @@ def main():
                        collective=("none" if world == 1 else
                                    f"fused into K5 ({fused.mode} into double-buffered symmetric memory) + one signal-pad barrier per step"
                                    if fused is not None else "nccl all_gather of corners+status per step"),
-                       frames_ok=n_ok, gather_equals_nccl_all_gather=gather_ok),
+                       frames_ok=n_ok, gather_equals_nccl_all_gather=gather_ok, numa_binding=numa),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * N * 16 + F * 12),
                 "d2h_bytes_per_step": int(F * ncorn * 12 + F * 4), "steps": Ke, "ms_per_step": e2e_ms,
@@ -589,7 +593,7 @@ def main():
         "scratch_mb": round(ex_scratch_mb(F, 8192, ncorn), 1), "staging_ring_mb": round(staging_mb(F), 1),
         "workload_gen_s": gen_s,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline:  # rank 0, at every N (with N>1 it is bound to one NUMA node: `cores` says how many)
         out["cpu_baseline"] = cpu_baseline_block(pts, clicks, args.cpu_sample_frames)
     print(json.dumps(out))
     if world > 1:

@@ -27,6 +27,37 @@ def init_from_env(backend: str | None = None):
     return rank, world, local
 
 
+def bind_to_gpu_numa(local_rank: int):
+    """Pin this process (and the threads / page-locked buffers it creates afterwards) to the CPUs of the NUMA node its
+    GPU hangs off, read from sysfs (/sys/bus/pci/devices/<bus id>/local_cpulist).  With one rank per GPU the host
+    buffers of every rank otherwise tend to land on one socket, and H2D copies of the other socket's GPUs cross the
+    inter-socket link.  Returns a short description, or None when nothing was changed."""
+    import subprocess
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        if len(bus.split(":")[0]) == 8:      # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
+            bus = bus[4:]
+        base = f"/sys/bus/pci/devices/{bus}"
+        cpus = set()
+        for part in open(f"{base}/local_cpulist").read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed or allowed == set(os.sched_getaffinity(0)):
+            return None
+        os.sched_setaffinity(0, allowed)
+        node = open(f"{base}/numa_node").read().strip()
+        return f"gpu {local_rank} ({bus}): numa node {node}, {len(allowed)} cpus"
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def shard_range(n_frames: int, world_size: int, rank: int):
     """Contiguous block of frames owned by `rank` (same arithmetic as ilcc2_shard_range in the C ABI)."""
     b = n_frames * rank // world_size
