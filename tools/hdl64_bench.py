@@ -10,7 +10,7 @@ pts, clicks = synth.make_batch(min(F, 32), scene=synth.SCENE_HDL64)
 reps = (F + pts.shape[0] - 1) // pts.shape[0]
 pts = np.ascontiguousarray(np.tile(pts, (reps, 1, 1))[:F]); clicks = np.ascontiguousarray(np.tile(clicks, (reps, 1))[:F])
 print(f"generated {min(F, 32)} distinct frames (tiled to {F}) in {time.time() - t:.1f} s", flush=True)
-ex = api.CornerExtractor(F, synth.HDL64.n_points, params=api.default_params(cells_x=8, cells_y=10))
+ex = api.CornerExtractor(F, synth.HDL64.n_points, params=api.default_params(cells_x=8, cells_y=10), roi_capacity=32768)
 dp, dc = torch.from_numpy(pts).cuda(), torch.from_numpy(clicks).cuda()
 for _ in range(3):
     st, c = ex.extract_torch(dp, dc, flags=api.FLAG_AUTO)
