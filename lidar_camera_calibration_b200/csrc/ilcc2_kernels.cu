@@ -406,7 +406,11 @@ __global__ void __launch_bounds__(kClusterThreads, SMEM ? 3 : 1) cluster_kernel(
   const int M = w.roi_count[f];
   // the shared-memory instantiation runs first and owns the frames that fit; it hands a frame over (sel_count = -1)
   // when its hash table gets too full
+#ifdef CLUSTER_FORCE_GLOBAL  // A/B: every frame on the global-memory tables
+  if (SMEM) return;
+#else
   if (SMEM ? (M > kClusterSmemPts) : (M <= kClusterSmemPts && w.sel_count[f] != -1)) return;
+#endif
   if (M == 0) {
     if (tid == 0) w.sel_count[f] = 0;
     return;
