@@ -1750,6 +1750,15 @@ struct ScalarWs {
 
 __device__ __forceinline__ double norm3(const double v[3]) { return dsqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
 
+// Read-modify-write of a warp-replicated scalar in shared memory (all 32 lanes hold and store the same value): every
+// lane must have READ the old value before any lane stores the new one.  Converged lanes do that anyway; the barriers
+// make it independent of convergence (compute-sanitizer's racecheck serialises lanes and does expose it otherwise).
+__device__ __forceinline__ void ws_update(double& dst, double v) {
+  __syncwarp();
+  dst = v;
+  __syncwarp();
+}
+
 __device__ __forceinline__ double quad3(const double H[6], const double u[3], const double v[3]) {
   const double h0 = H[0] * v[0] + H[1] * v[1] + H[2] * v[2];
   const double h1 = H[1] * v[0] + H[3] * v[1] + H[4] * v[2];
@@ -1905,9 +1914,10 @@ __device__ __noinline__ bool dogleg_build_model(Dogleg& S, const double Hs[6], c
   S.alpha = ddiv(S.grad[0] * S.grad[0] + S.grad[1] * S.grad[1] + S.grad[2] * S.grad[2], jg2);
   bool ok = false;
   double y[3] = {0.0, 0.0, 0.0};
-  while (S.mu < 1.0) {
+  double mu = S.mu;
+  while (mu < 1.0) {
     double A[6] = {Hs[0], Hs[1], Hs[2], Hs[3], Hs[4], Hs[5]};
-    const double sm = dsqrt(S.mu);
+    const double sm = dsqrt(mu);
     const double l0 = S.diag[0] * sm, l1 = S.diag[1] * sm, l2 = S.diag[2] * sm;
     A[0] += l0 * l0;
     A[3] += l1 * l1;
@@ -1916,8 +1926,9 @@ __device__ __noinline__ bool dogleg_build_model(Dogleg& S, const double Hs[6], c
       ok = true;
       break;
     }
-    S.mu *= 10.0;
+    mu *= 10.0;
   }
+  ws_update(S.mu, mu);
   if (!ok) return false;
   for (int i = 0; i < 3; ++i) S.gn[i] = -S.diag[i] * y[i];
   const double n_g = norm3(S.grad), n_n = norm3(S.gn);
@@ -2131,9 +2142,13 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
         scale[2] = ddiv(1.0, 1.0 + dsqrt(H[5]));
         best_cost = x_cost;
       } else {
-        if (quality < 0.25) S.radius *= 0.5;
-        if (quality > 0.75) S.radius = fmax(S.radius, 3.0 * S.step_norm);
-        S.mu = fmax(1e-8, ddiv(2.0 * S.mu, 10.0));
+        {
+          double r = S.radius;
+          if (quality < 0.25) r *= 0.5;
+          if (quality > 0.75) r = fmax(r, 3.0 * S.step_norm);
+          ws_update(S.radius, r);
+          ws_update(S.mu, fmax(1e-8, ddiv(2.0 * S.mu, 10.0)));
+        }
         S.reuse = 0;
         if (x_cost < best_cost) {
           best_cost = x_cost;
@@ -2143,18 +2158,20 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
     } else {
       succ = false;
       const double gnn = S.gnn;
-      const bool was_gn = gnn <= S.radius;
-      S.radius *= 0.5;
+      double r = S.radius;
+      const bool was_gn = gnn <= r;
+      r *= 0.5;
       S.reuse = 1;
       ++bi;
       if (was_gn) {
         // the identical Gauss-Newton candidate would be evaluated and rejected again
-        while (iter < max_iter && gnn <= S.radius && S.radius > 1e-32) {
+        while (iter < max_iter && gnn <= r && r > 1e-32) {
           iter++;
-          S.radius *= 0.5;
+          r *= 0.5;
           ++bi;
         }
       }
+      ws_update(S.radius, r);
     }
     first = false;
     // ---- next trust-region step (loops over invalid steps) ----
@@ -2225,7 +2242,7 @@ __device__ __forceinline__ int solve_tr(const FitPts<IdxT>* Fp, const VbModel* M
         break;
       }
       if (++invalid >= 5) { term = TERM_INVALID; stop = true; break; }
-      S.mu *= 10.0;
+      ws_update(S.mu, S.mu * 10.0);
       S.reuse = 0;
       nb = 0;
       succ = false;

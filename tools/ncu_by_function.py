@@ -22,6 +22,10 @@ def function_table(path):
                      r"[\w:<>\s\*&]*?\b(\w+)\s*\(")
     lines = open(path, errors="replace").read().split("\n")
     for i, ln in enumerate(lines, 1):
+        mk = re.match(r"^\s+(\w+_kernel)\(const Workspace", ln)  # kernel name on the line after its __launch_bounds__
+        if mk:
+            out.append((i, mk.group(1)))
+            continue
         if ln[:1] in (" ", "\t", "/", "#", "}", ""):
             continue
         m = pat.match(ln)
