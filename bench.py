@@ -7,7 +7,9 @@
 A "step" is one pass of the whole hot path (K1 roi_filter, K2 cluster, K3+K4 plane_pca, K5 board_fit, + the exchange of
 the corners between ranks when N>1: fused into K5 + one barrier, or an NCCL all-gather) over one batch of --frames
 synthetic VLP-16 frames per GPU (BASELINE.json configs[2]; 8 ranks x 1024 frames = configs[4]).  ONE JSON line (rank 0):
-  value            frames/s with the batch already resident in HBM (CUDA events around exactly K steps, max over ranks)
+  value            frames/s with the batch already resident in HBM (CUDA events around exactly K steps, max over ranks);
+                   consecutive steps are taken in turn by --lanes handles on streams of their own, so step k+1's kernels
+                   fill the tail of step k's K5; one_batch_in_flight is the same loop on one handle / one stream
   e2e              same metric through the C ABI with HOST buffers: pinned H2D of the batch + D2H of corners/status inside
                    the timed region; e2e_legs repeats it for pageable memory and for 32-byte PointCloud2 records
   roofline         dominant kernel of the step vs the measured HBM peak (algorithmic bytes = SURVEY.md 8(d));
@@ -306,6 +308,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the hdl64 / single-frame / pnp / projection legs")
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
                     help="multi-GPU exchange: auto = fused into K5 (multicast if available, else peer stores), nccl = all_gather")
+    ap.add_argument("--lanes", type=int, default=2,
+                    help="handles (each on its own CUDA stream) that take consecutive steps in turn; 1 = one batch in flight")
     ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin ranks to the NUMA node of their GPU")
     ap.add_argument("--watchdog-s", type=int, default=900, help="dump all stacks and exit if the run exceeds this")
     args = ap.parse_args()
@@ -313,6 +317,15 @@ def main():
     faulthandler.dump_traceback_later(args.watchdog_s, exit=True)
     if args.impl == "reference":
         return run_reference(args)
+
+    # stdout carries the ONE JSON line: whatever native libraries print there (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
     import torch
     from lidar_camera_calibration_b200 import api, dist as ldist, synth
@@ -330,12 +343,17 @@ def main():
         sampler.start()  # before the warm-up, so that it is up when the timed region starts
 
     pts, clicks, gt, gen_s = make_workload(F, rank * F, want_truth=True)
-    ex = api.CornerExtractor(F, N, device=local, roi_capacity=8192)
+    # `lanes` handles on streams of their own take the steps in turn (api.PipelinedExtractor): every step is the same
+    # launches on the same batch, but step k+1's kernels fill the SMs that the tail of step k's K5 leaves idle
+    L = max(1, args.lanes)
+    pipe = api.PipelinedExtractor(L, F, N, device=local, roi_capacity=8192)
+    ex = pipe.extractors[0]
     ncorn = ex.n_corners
     # device-resident inputs (value) and pinned host inputs (e2e)
     d_pts, d_clicks = torch.from_numpy(pts).to(dev), torch.from_numpy(clicks).to(dev)
-    d_corners = torch.empty((F, ncorn, 3), dtype=torch.float32, device=dev)
-    d_status = torch.empty((F,), dtype=torch.int32, device=dev)
+    lane_corners = [torch.empty((F, ncorn, 3), dtype=torch.float32, device=dev) for _ in range(L)]
+    lane_status = [torch.empty((F,), dtype=torch.int32, device=dev) for _ in range(L)]
+    d_corners, d_status = lane_corners[0], lane_status[0]
     h_pts, h_clicks = torch.from_numpy(pts).pin_memory(), torch.from_numpy(clicks).pin_memory()
     h_corners = torch.empty((F, ncorn, 3), dtype=torch.float32).pin_memory()
     h_status = torch.empty((F,), dtype=torch.int32).pin_memory()
@@ -343,35 +361,43 @@ def main():
 
     # multi-GPU exchange: K5 stores the corners straight into every rank's gather buffer over NVLink (one barrier per
     # step, no data-path collective); NCCL all-gather when symmetric memory is not available (--gather nccl forces it)
-    fused = None
+    fused_l = None   # one exchange object per lane: its own double-buffered symmetric buffer and signal pads
     if world > 1 and args.gather != "nccl":
         try:
-            fused = ldist.FusedGather(ex, F, ncorn, rank, world, dev, use_multicast=(args.gather != "peer"))
+            fused_l = [ldist.FusedGather(pipe.extractors[j], F, ncorn, rank, world, dev, use_multicast=(args.gather != "peer"))
+                       for j in range(L)]
         except Exception as e:  # noqa: BLE001
             if rank == 0:
                 print(f"[bench] fused gather unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
-            fused = None
+            fused_l = None
     if world > 1:
-        flag = torch.tensor([1 if fused is not None else 0], device=dev)
+        flag = torch.tensor([1 if fused_l is not None else 0], device=dev)
         torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
-        if int(flag.item()) == 0 and fused is not None:
-            fused.close()
-            fused = None
-    g_corners = torch.empty((world * F, ncorn, 3), dtype=torch.float32, device=dev) if world > 1 and fused is None else None
-    g_status = torch.empty((world * F,), dtype=torch.int32, device=dev) if world > 1 and fused is None else None
+        if int(flag.item()) == 0 and fused_l is not None:
+            for fg in fused_l:
+                fg.close()
+            fused_l = None
+    fused = fused_l[0] if fused_l is not None else None
+    nccl_gather = world > 1 and fused is None
+    lane_gc = [torch.empty((world * F, ncorn, 3), dtype=torch.float32, device=dev) for _ in range(L)] if nccl_gather else None
+    lane_gs = [torch.empty((world * F,), dtype=torch.int32, device=dev) for _ in range(L)] if nccl_gather else None
+    g_corners, g_status = (lane_gc[0], lane_gs[0]) if nccl_gather else (None, None)
 
     def gathered():
         return (fused.corners, fused.status) if fused is not None else (g_corners, g_status)
 
-    def exchange():
-        if fused is not None:
-            fused.barrier()
+    def exchange(j=0):  # on the current stream
+        if fused_l is not None:
+            fused_l[j].barrier()
         elif world > 1:
-            ldist.allgather_corners(d_corners, d_status, world, g_corners, g_status)
+            ldist.allgather_corners(lane_corners[j], lane_status[j], world, lane_gc[j], lane_gs[j])
 
     def step_device():
+        pipe.submit(d_pts, d_clicks, lane_corners, lane_status, flags=api.FLAG_AUTO, after=exchange if world > 1 else None)
+
+    def step_one_lane():
         ex.extract_torch(d_pts, d_clicks, d_corners, d_status, flags=api.FLAG_AUTO, stream=stream)
-        exchange()
+        exchange(0)
 
     def barrier():
         if world > 1:
@@ -386,21 +412,29 @@ def main():
         return ms
 
     # ---- device-resident throughput: exactly K steps, nothing else inside the timed region ----
-    for _ in range(W):
-        step_device()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = ex.launch_count
-    sampler.mark()
-    e0.record(stream)
-    for _ in range(K):
-        step_device()
-    e1.record(stream)
-    barrier()
-    sampler.mark()
-    elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = ex.launch_count - launches0
+    def timed(step, steps):
+        for _ in range(W):
+            step()
+        pipe.join(stream)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = pipe.launch_count
+        sampler.mark()
+        t0.record(stream)     # the lanes' streams wait for `stream` at every submit, i.e. they start behind t0
+        for _ in range(steps):
+            step()
+        pipe.join(stream)     # `stream` waits for the last step of every lane
+        t1.record(stream)
+        barrier()
+        sampler.mark()
+        return max_over_ranks(t0.elapsed_time(t1)), pipe.launch_count - n0
+
+    elapsed_ms, launches = timed(step_device, K)
     n_ok = int((d_status == 0).sum().item())
+    lanes_agree = all(torch.equal(lane_status[j], d_status) and
+                      torch.equal(torch.nan_to_num(lane_corners[j], nan=-1.0), torch.nan_to_num(d_corners, nan=-1.0)) for j in range(L))
+    # the same K steps with ONE batch in flight (one handle, one stream): what the overlap of consecutive steps is worth
+    one_lane_ms = timed(step_one_lane, K)[0] if L > 1 else elapsed_ms
 
     # ---- per-kernel times: a separate pass with the library's CUDA events around every stage (same stream) ----
     ex.set_profiling(True)
@@ -414,31 +448,55 @@ def main():
     exchange()  # keeps the ranks' double buffers in step
 
     # ---- end to end through the C ABI with host buffers (H2D + kernels + D2H every step) ----
-    def e2e_run(points_t, width, steps):
-        def one():
-            ex.extract_raw(points_t.data_ptr(), F, N, width, h_clicks.data_ptr(), h_corners.data_ptr(), h_status.data_ptr(),
-                           api.MEM_HOST, api.FLAG_AUTO, stream.cuda_stream)
-            if fused is not None:
-                fused.barrier()
-            elif world > 1:  # the call left this step's corners in the pinned host buffers: upload them, then gather
-                d_corners.copy_(h_corners, non_blocking=True)
-                d_status.copy_(h_status, non_blocking=True)
-                ldist.allgather_corners(d_corners, d_status, world, g_corners, g_status)
-        for _ in range(2):
-            one()
+    h_corners_l = [h_corners] + [torch.empty((F, ncorn, 3), dtype=torch.float32).pin_memory() for _ in range(L - 1)]
+    h_status_l = [h_status] + [torch.empty((F,), dtype=torch.int32).pin_memory() for _ in range(L - 1)]
+
+    def e2e_run(points_t, width, steps, lanes=L):
+        """The lanes take the steps in turn, each with a host thread in the blocking C-ABI call (PipelinedExtractor.submit_host);
+        a step's exchange is enqueued on its lane's stream once its call has returned."""
+        pending = [False] * L
+
+        def finish(j):  # step of lane j: call returned -> its exchange (this thread, lane j's stream)
+            pipe.wait_lane(j)
+            if pending[j] and world > 1:
+                with torch.cuda.stream(pipe.streams[j]):
+                    if fused_l is not None:
+                        fused_l[j].barrier()
+                    else:  # the call left this step's corners in the pinned host buffers: upload them, then gather
+                        lane_corners[j].copy_(h_corners_l[j], non_blocking=True)
+                        lane_status[j].copy_(h_status_l[j], non_blocking=True)
+                        ldist.allgather_corners(lane_corners[j], lane_status[j], world, lane_gc[j], lane_gs[j])
+            pending[j] = False
+
+        def run(n):
+            for _ in range(n):
+                j = pipe.next_lane
+                finish(j)
+                pipe.submit_host(points_t.data_ptr(), F, N, width, h_clicks.data_ptr(), h_corners_l[j].data_ptr(),
+                                 h_status_l[j].data_ptr(), api.FLAG_AUTO)
+                pending[j] = True
+            for j in range(L):
+                finish(j)
+            pipe.join(stream)
+            for j in range(L):
+                stream.wait_stream(pipe.streams[j])
+
+        pipe.active = lanes
+        run(2 * lanes)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
-        for _ in range(steps):
-            one()
+        run(steps)
         f1.record(stream)
         barrier()
+        pipe.active = L
         return max_over_ranks(f0.elapsed_time(f1)) / steps
 
     Ke = max(3, min(K, 10))
     sampler.mark()
     e2e_ms = e2e_run(h_pts, 4, Ke)
     sampler.mark()
+    e2e_one_ms = e2e_run(h_pts, 4, Ke, lanes=1) if L > 1 else e2e_ms
     e2e_match = bool(np.array_equal(h_corners.numpy(), d_corners.cpu().numpy(), equal_nan=True))
     clocks = sampler.stop() if rank == 0 else None
     legs = {"packed16_pinned": {"ms_per_step": e2e_ms, "frames_per_s": world * F / (e2e_ms * 1e-3),
@@ -568,12 +626,23 @@ def main():
                        collective=("none" if world == 1 else
                                    f"fused into K5 ({fused.mode} into double-buffered symmetric memory) + one signal-pad barrier per step"
                                    if fused is not None else "nccl all_gather of corners+status per step"),
-                       frames_ok=n_ok, gather_equals_nccl_all_gather=gather_ok, numa_binding=numa),
+                       frames_ok=n_ok, gather_equals_nccl_all_gather=gather_ok, numa_binding=numa,
+                       pipeline=f"{L} handles x {L} CUDA streams take the K steps in turn (api.PipelinedExtractor); every step = the "
+                                "same launches on the same batch, consecutive steps overlap on the device" if L > 1 else
+                                "one handle, one stream: one batch in flight"),
+        "one_batch_in_flight": {"value": world * F * K / (one_lane_ms * 1e-3), "ms_per_step": one_lane_ms / K, "unit": UNIT,
+                                "note": "the same K steps on one handle and one stream (no overlap of consecutive steps); "
+                                        "kernel_ms_per_step and the rooflines are measured this way",
+                                "lanes_agree": lanes_agree},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * N * 16 + F * 12),
                 "d2h_bytes_per_step": int(F * ncorn * 12 + F * 4), "steps": Ke, "ms_per_step": e2e_ms,
-                "api": "ilcc2_extract_corners(mem_kind=ILCC2_MEM_HOST), pinned host buffers, packed 16-byte records",
-                "matches_device_path": e2e_match},
+                "api": "ilcc2_extract_corners(mem_kind=ILCC2_MEM_HOST), pinned host buffers, packed 16-byte records; "
+                       f"{L} handles, each with a host thread in the blocking call, take the steps in turn",
+                "matches_device_path": e2e_match,
+                "one_call_in_flight": {"ms_per_step": e2e_one_ms, "value": world * F / (e2e_one_ms * 1e-3)},
+                "pcie_floor_ms": (F * N * 16 + F * 12) / 55e9 * 1e3,
+                "pcie_floor_note": "H2D bytes of a step at 55 GB/s (PCIe Gen5 x16 in practice)"},
         "e2e_legs": legs,
         "gpu_launches": int(launches),
         "roofline": roofline,
@@ -595,7 +664,7 @@ def main():
     }
     if not args.no_cpu_baseline:  # rank 0, at every N (with N>1 it is bound to one NUMA node: `cores` says how many)
         out["cpu_baseline"] = cpu_baseline_block(pts, clicks, args.cpu_sample_frames)
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -493,3 +493,39 @@ def test_sparse_roi_overflows_the_shared_memory_cell_table(api, oracle):
         for k in ("n_roi", "n_clusters", "click_in_cluster", "cluster_rank", "n_cluster_pts"):
             assert diags[f][k] == d_o[k], (k, diags[f][k], d_o[k])
         assert d_o["n_clusters"] >= 1 and np.array_equal(ex.fetch_indices(f, 1), clu_o)
+
+
+@pytest.mark.gpu
+def test_pipelined_lanes_deliver_what_one_handle_delivers(api):
+    """api.PipelinedExtractor (throughput mode: consecutive batches taken in turn by handles on streams of their own, and
+    by host threads for host buffers): every batch of a stream of DIFFERENT batches comes back exactly as one handle
+    computes it, whichever lane took it and whatever overlapped it on the device."""
+    import torch
+    from lidar_camera_calibration_b200 import synth
+    F, B = 96, 5
+    N = synth.VLP16.n_points
+    batches = [synth.make_batch(F, start=1000 + 37 * b) for b in range(B)]
+    ex = api.CornerExtractor(F, N, roi_capacity=8192)
+    want = [ex.extract(p, c, flags=api.FLAG_AUTO) for p, c in batches]
+    ex.close()
+    pipe = api.PipelinedExtractor(2, F, N, roi_capacity=8192)
+    dev = torch.device("cuda", 0)
+    d_in = [(torch.from_numpy(p).to(dev), torch.from_numpy(c).to(dev)) for p, c in batches]
+    d_out = [(torch.empty((F, pipe.n_corners, 3), dtype=torch.float32, device=dev),
+              torch.empty((F,), dtype=torch.int32, device=dev)) for _ in range(B)]
+    lanes = [pipe.submit(p, c, d_out[b][0], d_out[b][1]) for b, (p, c) in enumerate(d_in)]
+    assert lanes == [0, 1, 0, 1, 0]
+    pipe.join()
+    torch.cuda.synchronize()
+    for b in range(B):
+        assert np.array_equal(d_out[b][1].cpu().numpy(), want[b][0])
+        assert np.array_equal(d_out[b][0].cpu().numpy(), want[b][1], equal_nan=True)
+    # host buffers (pageable numpy memory), one host thread per lane
+    h_out = [(np.full((F, pipe.n_corners, 3), -7.0, np.float32), np.full(F, -7, np.int32)) for _ in range(B)]
+    for b, (p, c) in enumerate(batches):
+        pipe.submit_host(p.ctypes.data, F, N, 4, c.ctypes.data, h_out[b][0].ctypes.data, h_out[b][1].ctypes.data)
+    pipe.wait_all()
+    for b in range(B):
+        assert np.array_equal(h_out[b][1], want[b][0])
+        assert np.array_equal(h_out[b][0], want[b][1], equal_nan=True)
+    pipe.close()
