@@ -308,7 +308,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the hdl64 / single-frame / pnp / projection legs")
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
                     help="multi-GPU exchange: auto = fused into K5 (multicast if available, else peer stores), nccl = all_gather")
-    ap.add_argument("--lanes", type=int, default=2,
+    ap.add_argument("--lanes", type=int, default=3,
                     help="handles (each on its own CUDA stream) that take consecutive steps in turn; 1 = one batch in flight")
     ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin ranks to the NUMA node of their GPU")
     ap.add_argument("--watchdog-s", type=int, default=900, help="dump all stacks and exit if the run exceeds this")
@@ -434,17 +434,24 @@ def main():
     lanes_agree = all(torch.equal(lane_status[j], d_status) and
                       torch.equal(torch.nan_to_num(lane_corners[j], nan=-1.0), torch.nan_to_num(d_corners, nan=-1.0)) for j in range(L))
     # the same K steps with ONE batch in flight (one handle, one stream): what the overlap of consecutive steps is worth
+    ex.set_lanes(1)
     one_lane_ms = timed(step_one_lane, K)[0] if L > 1 else elapsed_ms
 
     # ---- per-kernel times: a separate pass with the library's CUDA events around every stage (same stream) ----
-    ex.set_profiling(True)
-    stage_ms = {s: 0.0 for s in api.STAGES}
+    def stage_pass():
+        ex.set_profiling(True)
+        acc = {s: 0.0 for s in api.STAGES}
+        for _ in range(Kp):
+            ex.extract_torch(d_pts, d_clicks, d_corners, d_status, flags=api.FLAG_AUTO, stream=stream)
+            for s, ms in ex.stage_times().items():
+                acc[s] += ms / Kp
+        ex.set_profiling(False)
+        return acc
+
     Kp = max(5, min(K, 20))
-    for _ in range(Kp):
-        ex.extract_torch(d_pts, d_clicks, d_corners, d_status, flags=api.FLAG_AUTO, stream=stream)
-        for s, ms in ex.stage_times().items():
-            stage_ms[s] += ms / Kp
-    ex.set_profiling(False)
+    stage_ms = stage_pass()            # one batch in flight: the launch shapes of a single handle (K5: 2 warps per solve)
+    ex.set_lanes(L)
+    stage_ms_lane = stage_pass() if L > 1 else stage_ms   # the shapes the lanes run (K5: 1 warp per solve), timed alone
     exchange()  # keeps the ranks' double buffers in step
 
     # ---- end to end through the C ABI with host buffers (H2D + kernels + D2H every step) ----
@@ -497,6 +504,22 @@ def main():
     e2e_ms = e2e_run(h_pts, 4, Ke)
     sampler.mark()
     e2e_one_ms = e2e_run(h_pts, 4, Ke, lanes=1) if L > 1 else e2e_ms
+
+    def h2d_only(steps):
+        """The floor of the end-to-end figure on THIS box: nothing but the step's H2D copy (page-locked -> device), all
+        ranks copying at the same time like in the end-to-end loop."""
+        scratch = torch.empty_like(d_pts)
+        scratch.copy_(h_pts, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(steps):
+            scratch.copy_(h_pts, non_blocking=True)
+        c1.record(stream)
+        barrier()
+        return max_over_ranks(c0.elapsed_time(c1)) / steps
+
+    h2d_ms = h2d_only(Ke)
     e2e_match = bool(np.array_equal(h_corners.numpy(), d_corners.cpu().numpy(), equal_nan=True))
     clocks = sampler.stop() if rank == 0 else None
     legs = {"packed16_pinned": {"ms_per_step": e2e_ms, "frames_per_s": world * F / (e2e_ms * 1e-3),
@@ -600,7 +623,10 @@ def main():
         parity = O.parity_report(pts, clicks, st_h, c_h, diags, threads=host_threads())
         parity["note"] = ("oracle (parity build) on ALL frames of the step's batch vs the C ABI's results; corners compared "
                           "index for index, tolerance = north_star's 1e-3 m")
-        parity["host_path_equals_device_path"] = bool(np.array_equal(c_h, d_corners.cpu().numpy(), equal_nan=True))
+        c_d = d_corners.cpu().numpy()
+        parity["host_path_equals_device_path"] = bool(np.array_equal(c_h, c_d, equal_nan=True))
+        both = np.isfinite(c_h).all(axis=(1, 2)) & np.isfinite(c_d).all(axis=(1, 2))
+        parity["host_vs_device_max_diff_m"] = float(np.abs(c_h[both] - c_d[both]).max()) if both.any() else None
 
     value = world * F * K / (elapsed_ms * 1e-3)
     e2e_value = world * F / (e2e_ms * 1e-3)
@@ -641,8 +667,9 @@ def main():
                        f"{L} handles, each with a host thread in the blocking call, take the steps in turn",
                 "matches_device_path": e2e_match,
                 "one_call_in_flight": {"ms_per_step": e2e_one_ms, "value": world * F / (e2e_one_ms * 1e-3)},
-                "pcie_floor_ms": (F * N * 16 + F * 12) / 55e9 * 1e3,
-                "pcie_floor_note": "H2D bytes of a step at 55 GB/s (PCIe Gen5 x16 in practice)"},
+                "h2d_copy_only_ms": h2d_ms, "h2d_copy_only_gbs_per_gpu": F * N * 16 / (h2d_ms * 1e-3) / 1e9,
+                "h2d_copy_only_note": "the step's 472 MB cudaMemcpyAsync from page-locked memory and nothing else, all ranks at "
+                                      "the same time: the floor of e2e on this box (the ranks share the host's PCIe / memory path)"},
         "e2e_legs": legs,
         "gpu_launches": int(launches),
         "roofline": roofline,
@@ -651,15 +678,18 @@ def main():
                             note="the only kernel that reads all input bytes"),
         "roofline_compute": ncu_compute_ceilings(),
         "kernel_ms_per_step": stage_ms,
-        "kernel_ms_note": "CUDA events of the library around each stage, a separate pass of the same workload (the timed "
-                          "region of `value` holds nothing but the K steps)",
+        "kernel_ms_note": "CUDA events of the library around each stage, a separate pass of the same workload with ONE batch in "
+                          "flight (the timed region of `value` holds nothing but the K steps)",
+        "kernel_ms_per_step_lane_shapes": stage_ms_lane,
+        "kernel_ms_lane_shapes_note": "the same pass with the launch shapes the lanes use (ilcc2_set_lanes: K5 with one warp per "
+                                      "solve -- slower for a batch on its own, faster when consecutive batches overlap)",
         "parity": parity,
         "accuracy_vs_truth_m": accuracy,
         "single_frame_latency_ms": single_ms,
         "hdl64": hdl,
         "pnp": pnp,
         "projection": proj,
-        "scratch_mb": round(ex_scratch_mb(F, 8192, ncorn), 1), "staging_ring_mb": round(staging_mb(F), 1),
+        "scratch_mb": round(ex_scratch_mb(F, 8192, ncorn), 1), "staging_ring_mb": round(staging_mb(F), 1), "handles": L,
         "workload_gen_s": gen_s,
     }
     if not args.no_cpu_baseline:  # rank 0, at every N (with N>1 it is bound to one NUMA node: `cores` says how many)

@@ -176,6 +176,16 @@ int ilcc2_fetch_board_points(ilcc2_handle* h, int frame, float* yz_out_host, uin
 int ilcc2_set_profiling(ilcc2_handle* h, int enabled);
 int ilcc2_stage_times(ilcc2_handle* h, float* ms_out, const char** names_out, int cap);
 
+/* Throughput mode for a STREAM of device-resident batches: `lanes` handles, each with a CUDA stream of its own, take
+ * consecutive batches in turn (ilcc2_extract_corners is asynchronous for ILCC2_MEM_DEVICE), so that the kernels of batch
+ * k+1 run on the SMs that the tail of batch k's K5 leaves idle.  This call tells a handle that it is one of `lanes` such
+ * handles: launch shapes that depend on how many frames are in flight on the device (K5's warps per solve) are then
+ * chosen for lanes x the call's frames.  Results do not depend on it (same launches, same arithmetic; the partial sums
+ * of a solve are grouped by its warps, which moves theta/t in the 15th digit and leaves the fp32 corners as they are).
+ * lanes = 1 (default): one batch in flight.  The reference processes one cloud at a time (get_lidar_corners.cpp:136-198);
+ * this is the batch-stream counterpart of its bag loop. */
+int ilcc2_set_lanes(ilcc2_handle* h, int lanes);
+
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t ilcc2_launch_count(const ilcc2_handle* h);
 

@@ -20,7 +20,7 @@ EXPORTS = [
     "ilcc2_pnp_order_corners", "ilcc2_pnp_solve", "ilcc2_compose_extrinsic", "ilcc2_extrinsic2bin",
     "ilcc2_read_cam_corners", "ilcc2_read_lidar_corners", "ilcc2_read_camera_yaml", "ilcc2_project_points",
     "ilcc2_set_gather_targets", "ilcc2_create_sized", "ilcc2_gather_setup_nccl", "ilcc2_gather_sync",
-    "ilcc2_gather_is_fused", "ilcc2_gather_teardown",
+    "ilcc2_gather_is_fused", "ilcc2_gather_teardown", "ilcc2_set_lanes",
 ]
 
 
@@ -90,6 +90,8 @@ def load() -> C.CDLL:
     L.ilcc2_fetch_indices.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
     L.ilcc2_fetch_board_points.restype = C.c_int
     L.ilcc2_fetch_board_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.ilcc2_set_lanes.restype = C.c_int
+    L.ilcc2_set_lanes.argtypes = [C.c_void_p, C.c_int]
     L.ilcc2_set_profiling.restype = C.c_int
     L.ilcc2_set_profiling.argtypes = [C.c_void_p, C.c_int]
     L.ilcc2_stage_times.restype = C.c_int

@@ -193,6 +193,10 @@ class CornerExtractor:
             raise Ilcc2Error(f"ilcc2_fetch_board_points failed ({n})")
         return yz[:n].copy(), wh[:n].copy()
 
+    def set_lanes(self, lanes: int):
+        """ilcc2_set_lanes: this handle is one of `lanes` handles that take consecutive device-resident batches in turn."""
+        self._check(self._L.ilcc2_set_lanes(self._h, int(lanes)))
+
     def set_profiling(self, enabled: bool):
         self._check(self._L.ilcc2_set_profiling(self._h, int(enabled)))
 
@@ -225,6 +229,8 @@ class PipelinedExtractor:
         import torch
         self.device = torch.device("cuda", device)
         self.extractors = [CornerExtractor(max_frames, max_points_per_frame, device=device, **kw) for _ in range(lanes)]
+        for e in self.extractors:
+            e.set_lanes(lanes)
         self.streams = [torch.cuda.Stream(self.device) for _ in range(lanes)]
         self._ready = [torch.cuda.Event() for _ in range(lanes)]
         self._done = [torch.cuda.Event() for _ in range(lanes)]

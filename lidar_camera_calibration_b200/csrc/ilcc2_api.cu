@@ -176,6 +176,7 @@ struct ilcc2_handle {
   cudaStream_t work_stream[kWorkStreams] = {};
   cudaEvent_t ev_work_done[kWorkStreams] = {};
   int e2e_chunk_frames = 64;
+  int lanes = 1;             // ilcc2_set_lanes: handles that take consecutive device-resident batches in turn
   int dev_chunks = 1;        // > 1 (ILCC2_DEV_CHUNKS): device-resident batches are cut into this many concurrent chunks
   bool ev_valid = false;
   int64_t launches = 0;
@@ -678,6 +679,7 @@ int ilcc2_extract_corners(ilcc2_handle* h, const void* points, int n_frames, int
     w.frame_base = cb[c];
     w.n_frames = cn[c];
     w.load_frames = dev_chunked ? n_frames : cn[c];
+    if (!host) w.load_frames *= h->lanes;  // other handles' batches are in flight next to this one
     cudaStream_t cs = multi ? h->work_stream[c % ilcc2_handle::kWorkStreams] : s;
     const int ds = c % ilcc2_handle::kDevSlots;
     if (host) {
@@ -786,6 +788,13 @@ int ilcc2_fetch_board_points(ilcc2_handle* h, int frame, float* yz_out_host, uin
       return -ILCC2_ERR_CUDA;
   }
   return n;
+}
+
+int ilcc2_set_lanes(ilcc2_handle* h, int lanes) {
+  if (!h) return ILCC2_ERR_INVALID_ARGUMENT;
+  if (lanes < 1 || lanes > 64) return fail(h, ILCC2_ERR_INVALID_ARGUMENT, "lanes must be in [1, 64]");
+  h->lanes = lanes;
+  return ILCC2_SUCCESS;
 }
 
 int ilcc2_set_profiling(ilcc2_handle* h, int enabled) {

@@ -11,6 +11,8 @@ pts, clicks = synth.make_batch(F)
 d_pts, d_clicks = torch.from_numpy(pts).to(dev), torch.from_numpy(clicks).to(dev)
 ref = None
 CASES = ((1, False), (2, False)) if os.environ.get('PIPE_SHORT') else ((1, False), (2, False), (2, True), (3, False), (4, False))
+if os.environ.get('PIPE_CASES'):
+    CASES = tuple((int(x), False) for x in os.environ['PIPE_CASES'].split(','))
 for D, prio in CASES:
     exs = [api.CornerExtractor(F, synth.VLP16.n_points, roi_capacity=8192) for _ in range(D)]
     streams = [torch.cuda.Stream(dev, priority=(-1 if (prio and i % 2 == 0) else 0)) for i in range(D)]
