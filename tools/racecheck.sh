@@ -1,6 +1,6 @@
 #!/bin/bash
 # racecheck of one pass over 24 frames; per severity the distinct (write site, read/write site) pairs
-timeout 900 compute-sanitizer --tool racecheck --racecheck-report all --print-limit 200000 python tools/profile_step.py 1 24 > /tmp/race.log 2>&1
+timeout 900 compute-sanitizer --tool racecheck --racecheck-report all --print-limit 200000 python tools/profile_step.py 1 24 $1 > /tmp/race.log 2>&1
 grep -E "RACECHECK SUMMARY" /tmp/race.log
 python - <<'PY'
 import re, collections
