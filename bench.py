@@ -310,6 +310,10 @@ def main():
                     help="multi-GPU exchange: auto = fused into K5 (multicast if available, else peer stores), nccl = all_gather")
     ap.add_argument("--lanes", type=int, default=3,
                     help="handles (each on its own CUDA stream) that take consecutive steps in turn; 1 = one batch in flight")
+    ap.add_argument("--gather-parts", type=int, default=0, choices=[0, 2, 3],
+                    help="parts of every lane's symmetric gather buffer: 3 = the signal-pad barrier runs on a side stream, one "
+                         "step behind the lane (dist.FusedGather); 2 = inline on the lane's stream; 0 = 3 from four ranks on "
+                         "(measured 1.78 -> 1.75 ms per step at N=4, 1.83 -> 1.78 at N=8; at N=2 inline is faster: 1.73 vs 1.77)")
     ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin ranks to the NUMA node of their GPU")
     ap.add_argument("--watchdog-s", type=int, default=900, help="dump all stacks and exit if the run exceeds this")
     args = ap.parse_args()
@@ -330,6 +334,8 @@ def main():
     import torch
     from lidar_camera_calibration_b200 import api, dist as ldist, synth
     rank, world, local = ldist.init_from_env()
+    if args.gather_parts == 0:
+        args.gather_parts = 3 if world >= 4 else 2
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
@@ -364,8 +370,8 @@ def main():
     fused_l = None   # one exchange object per lane: its own double-buffered symmetric buffer and signal pads
     if world > 1 and args.gather != "nccl":
         try:
-            fused_l = [ldist.FusedGather(pipe.extractors[j], F, ncorn, rank, world, dev, use_multicast=(args.gather != "peer"))
-                       for j in range(L)]
+            fused_l = [ldist.FusedGather(pipe.extractors[j], F, ncorn, rank, world, dev, use_multicast=(args.gather != "peer"),
+                                         halves=args.gather_parts) for j in range(L)]
         except Exception as e:  # noqa: BLE001
             if rank == 0:
                 print(f"[bench] fused gather unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
@@ -383,8 +389,16 @@ def main():
     lane_gs = [torch.empty((world * F,), dtype=torch.int32, device=dev) for _ in range(L)] if nccl_gather else None
     g_corners, g_status = (lane_gc[0], lane_gs[0]) if nccl_gather else (None, None)
 
-    def gathered():
-        return (fused.corners, fused.status) if fused is not None else (g_corners, g_status)
+    def gathered():  # for a consumer on the current stream
+        if fused is not None:
+            fused.wait_ready()
+            return fused.corners, fused.status
+        return g_corners, g_status
+
+    def exchanges_done(s):  # `s` waits for the last barrier of every lane (they may run on side streams)
+        if fused_l is not None:
+            for fg in fused_l:
+                fg.wait_ready(s)
 
     def exchange(j=0):  # on the current stream
         if fused_l is not None:
@@ -423,7 +437,8 @@ def main():
         t0.record(stream)     # the lanes' streams wait for `stream` at every submit, i.e. they start behind t0
         for _ in range(steps):
             step()
-        pipe.join(stream)     # `stream` waits for the last step of every lane
+        pipe.join(stream)     # `stream` waits for the last step of every lane ...
+        exchanges_done(stream)  # ... and for its exchange
         t1.record(stream)
         barrier()
         sampler.mark()
@@ -487,6 +502,7 @@ def main():
             pipe.join(stream)
             for j in range(L):
                 stream.wait_stream(pipe.streams[j])
+            exchanges_done(stream)
 
         pipe.active = lanes
         run(2 * lanes)
@@ -552,6 +568,8 @@ def main():
             gc, gs = gathered()
             ref_c, ref_s = ldist.allgather_corners(d_corners, d_status, world)
             same = same and torch.equal(ref_s, gs) and torch.equal(torch.nan_to_num(ref_c, nan=-1.0), torch.nan_to_num(gc, nan=-1.0))
+            if fused is not None:
+                fused.release()
         t = torch.tensor([1 if same else 0], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
         gather_ok = bool(t.item())
@@ -650,7 +668,8 @@ def main():
         "config": dict(base_config(args, world),
                        l2=f"inputs {F * N * 16 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
                        collective=("none" if world == 1 else
-                                   f"fused into K5 ({fused.mode} into double-buffered symmetric memory) + one signal-pad barrier per step"
+                                   f"fused into K5 ({fused.mode} into {args.gather_parts}-part symmetric memory per lane) + one signal-pad barrier per step"
+                                   + (" on a side stream, one step behind the lane" if args.gather_parts == 3 else "")
                                    if fused is not None else "nccl all_gather of corners+status per step"),
                        frames_ok=n_ok, gather_equals_nccl_all_gather=gather_ok, numa_binding=numa,
                        pipeline=f"{L} handles x {L} CUDA streams take the K steps in turn (api.PipelinedExtractor); every step = the "

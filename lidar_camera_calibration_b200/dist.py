@@ -96,59 +96,112 @@ def allgather_rows(x, world_size: int):
 class FusedGather:
     """The all-gather of the per-frame corners fused into the kernel that produces them.
 
-    Every rank owns a symmetric-memory buffer of TWO halves [2][world * F_local frames]
+    Every rank owns a symmetric-memory buffer of `halves` parts [halves][world * F_local frames]
     (torch.distributed._symmetric_memory: the allocations of all ranks are mapped into each other's address space over
-    NVLink); K5 stores frame f of rank r into slot r * F_local + f of EVERY rank's current half
+    NVLink); K5 stores frame f of rank r into slot r * F_local + f of EVERY rank's current part
     (ilcc2_set_gather_targets) -- through the NVLS multicast mapping with one multimem.st per value when the fabric
     offers it, else with one plain store per peer.  barrier() is the only cross-rank operation of a step: a signal-pad
-    barrier, no data moves through a collective.  It also flips to the other half for the next step, so a rank that
-    runs ahead cannot overwrite corners another rank is still reading: it reaches this half again only after the NEXT
-    barrier, which every rank enters after it has consumed this step (consume(k) precedes produce(k+1) in stream order).
-    `corners` / `status` always name the half the last barrier() completed.
+    barrier, no data moves through a collective.
+
+    halves = 2 (default): barrier() runs on the current stream and flips to the other part for the next step, so a rank
+    that runs ahead cannot overwrite corners another rank is still reading: it reaches this part again only after the
+    NEXT barrier, which every rank enters after it has consumed this step (consume(k) precedes produce(k+1) in stream
+    order).  `corners` / `status` name the part the last barrier() completed.
+
+    halves = 3 (deferred): barrier() only records the producer on the current stream; the signal-pad barrier itself runs
+    on a side stream, so the ranks' skew is absorbed while the current stream already works on its next step.  Step k
+    writes part k mod 3; produce(k+3) overwrites it and needs every rank's consume(k) to be over: consume(k) is
+    enqueued behind barrier(k) (wait_ready) and therefore ahead of barrier(k+1) on each rank's side stream, so the
+    current stream waits for ITS barrier(k+1) before produce(k+3) -- i.e. barrier() of step k ends with a wait for the
+    barrier of step k-1, which guards the next produce.  A consumer calls wait_ready(stream), reads `corners` / `status`
+    (the part of the last step handed to barrier()) on that stream, and calls release(stream), which puts the read
+    ahead of the next barrier on the side stream.
 
     Raises if symmetric memory cannot be set up; callers fall back to allgather_corners (NCCL)."""
 
     def __init__(self, extractor, frames_local: int, n_corners: int, rank: int, world: int, device,
-                 use_multicast: bool = True):
+                 use_multicast: bool = True, halves: int = 2):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
-        self.world, self.rank, self.F, self.ncorn = world, rank, frames_local, n_corners
+        assert halves in (2, 3)
+        self.world, self.rank, self.F, self.ncorn, self.halves = world, rank, frames_local, n_corners, halves
         total = world * frames_local
         cbytes = total * n_corners * 3 * 4
         half = (cbytes + total * 4 + 255) // 256 * 256
-        self.buf = symm.empty((2 * half,), dtype=torch.uint8, device=device)
+        self.buf = symm.empty((halves * half,), dtype=torch.uint8, device=device)
         self.buf.zero_()
         self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
         self._views = []
-        for k in range(2):
+        for k in range(halves):
             b = self.buf[k * half:(k + 1) * half]
             self._views.append((b[:cbytes].view(torch.float32).view(total, n_corners, 3),
                                 b[cbytes:cbytes + total * 4].view(torch.int32)))
         mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if use_multicast else 0
         if mc:
             self.mode, self._kind = "nvls multicast, multimem.st", 1
-            self._targets = [([mc + k * half], [mc + k * half + cbytes]) for k in range(2)]
+            self._targets = [([mc + k * half], [mc + k * half + cbytes]) for k in range(halves)]
         else:
             self.mode, self._kind = "peer stores", 0
             bases = [int(p) for p in self.hdl.buffer_ptrs]
-            self._targets = [([p + k * half for p in bases], [p + k * half + cbytes for p in bases]) for k in range(2)]
+            self._targets = [([p + k * half for p in bases], [p + k * half + cbytes for p in bases]) for k in range(halves)]
         self._extractor, self._slot, self._half = extractor, rank * frames_local, 0
         self.corners, self.status = self._views[0]
         self._point(0)
         self.hdl.barrier(channel=0)
+        if halves == 3:
+            self._side = torch.cuda.Stream(device)
+            self._produced = torch.cuda.Event()
+            self._bar_events = [torch.cuda.Event(), torch.cuda.Event()]   # barrier(k) -> slot k & 1
+            self._steps = 0
+            torch.cuda.current_stream(device).synchronize()
 
     def _point(self, k: int):
         c, s = self._targets[k]
         self._extractor.set_gather_targets(c, s, self._slot, self._kind)
 
     def barrier(self):
-        """All ranks' stores of this step are visible in every rank's buffer afterwards (runs on the current stream);
-        the next step's stores go to the other half."""
-        self.hdl.barrier(channel=0)
+        """halves = 2: all ranks' stores of this step are visible in every rank's buffer afterwards (runs on the current
+        stream); the next step's stores go to the other part.  halves = 3: the same barrier, on the side stream (see the
+        class comment); the current stream only waits for the barrier of the PREVIOUS step."""
+        import torch
+        if self.halves == 2:
+            self.hdl.barrier(channel=0)
+            self.corners, self.status = self._views[self._half]
+            self._half ^= 1
+            self._point(self._half)
+            return
+        cur = torch.cuda.current_stream(self.buf.device)
+        k = self._steps
+        self._produced.record(cur)
+        self._side.wait_event(self._produced)
+        with torch.cuda.stream(self._side):
+            self.hdl.barrier(channel=0)
+        self._bar_events[k & 1].record(self._side)
+        if k >= 1:
+            cur.wait_event(self._bar_events[(k - 1) & 1])   # guards produce(k+1) ... produce(k+2) on this stream
         self.corners, self.status = self._views[self._half]
-        self._half ^= 1
+        self._half = (self._half + 1) % 3
         self._point(self._half)
+        self._steps = k + 1
+
+    def wait_ready(self, stream=None):
+        """Make `stream` (default: current) wait until `corners` / `status` hold every rank's results of the last step
+        given to barrier().  A no-op with halves = 2 when the consumer runs on the stream barrier() ran on."""
+        import torch
+        if self.halves == 3 and self._steps > 0:
+            s = stream if stream is not None else torch.cuda.current_stream(self.buf.device)
+            s.wait_event(self._bar_events[(self._steps - 1) & 1])
+
+    def release(self, stream=None):
+        """The reads of `corners` / `status` enqueued on `stream` so far come before this rank's next barrier (halves = 3;
+        with halves = 2 stream order already says so when the consumer runs on the stream of barrier())."""
+        import torch
+        if self.halves == 3:
+            s = stream if stream is not None else torch.cuda.current_stream(self.buf.device)
+            ev = torch.cuda.Event()
+            ev.record(s)
+            self._side.wait_event(ev)
 
     def close(self):
         self._extractor.set_gather_targets([], [], 0)

@@ -15,6 +15,8 @@ if os.environ.get('PIPE_CASES'):
     CASES = tuple((int(x), False) for x in os.environ['PIPE_CASES'].split(','))
 for D, prio in CASES:
     exs = [api.CornerExtractor(F, synth.VLP16.n_points, roi_capacity=8192) for _ in range(D)]
+    for e in exs:
+        e.set_lanes(int(os.environ.get('PIPE_SET_LANES', D)))
     streams = [torch.cuda.Stream(dev, priority=(-1 if (prio and i % 2 == 0) else 0)) for i in range(D)]
     outs = [(torch.empty((F, exs[0].n_corners, 3), dtype=torch.float32, device=dev), torch.empty((F,), dtype=torch.int32, device=dev)) for _ in range(D)]
     def run(steps):
