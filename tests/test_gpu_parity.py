@@ -364,6 +364,37 @@ def test_bench_batch_parity_with_the_oracle(api, oracle):
     assert rep["hyp_equal_frac"] == 1.0 and rep["iters_equal_frac"] >= 0.995 and rep["term_equal_frac"] >= 0.995, rep
 
 
+@pytest.mark.parametrize("lanes", [1, 3])
+def test_bench_batch_device_path_parity_with_the_oracle(api, oracle, lanes):
+    """The same batch through the DEVICE path, i.e. exactly the launches bench.py's `value` times: one launch of 1024
+    frames with K5 on two warps per solve (lanes = 1: one batch in flight) and on one warp per solve (ilcc2_set_lanes(3):
+    the shape of the throughput mode), diag records read back from device memory."""
+    import ctypes as C
+    import os
+    import torch
+    from lidar_camera_calibration_b200 import synth, _lib
+    F = 1024
+    pts, clicks = synth.make_batch(F, start=0)
+    ex = api.CornerExtractor(F, synth.VLP16.n_points, roi_capacity=8192)
+    ex.set_lanes(lanes)
+    dp, dc = torch.from_numpy(pts).cuda(), torch.from_numpy(clicks).cuda()
+    corners = torch.empty((F, ex.n_corners, 3), dtype=torch.float32, device="cuda")
+    status = torch.empty((F,), dtype=torch.int32, device="cuda")
+    dbuf = torch.zeros((F * C.sizeof(_lib.Diag),), dtype=torch.uint8, device="cuda")
+    ex.extract_raw(dp.data_ptr(), F, synth.VLP16.n_points, 4, dc.data_ptr(), corners.data_ptr(), status.data_ptr(),
+                   api.MEM_DEVICE, api.FLAG_AUTO, torch.cuda.current_stream().cuda_stream, diag_ptr=dbuf.data_ptr())
+    torch.cuda.synchronize()
+    diags = (_lib.Diag * F).from_buffer_copy(dbuf.cpu().numpy().tobytes())
+    diags = [api.diag_to_dict(d) for d in diags]
+    rep = oracle.parity_report(pts, clicks, status.cpu().numpy(), corners.cpu().numpy(), diags,
+                               threads=max(1, len(os.sched_getaffinity(0))))
+    print(f"parity (bench batch, device path, lanes {lanes}):", rep)
+    assert rep["status_equal"], rep
+    assert rep["max_corner_err_m"] <= TOL_CORNER_M and rep["frac_within_1e-3"] == 1.0, rep
+    assert rep["hyp_equal_frac"] == 1.0 and rep["iters_equal_frac"] >= 0.995 and rep["term_equal_frac"] >= 0.995, rep
+    assert rep["max_theta_t_diff"] < 1e-9, rep
+
+
 def test_hdl64_batch_parity_with_the_oracle(api, oracle):
     """32 HDL-64-like frames (64 x 2048 points, 9x7 board; BASELINE.json configs[3]) against the oracle."""
     import os
