@@ -35,7 +35,7 @@ constexpr int kClusterSmemPts = 4096; // K2: frames with at most this many ROI p
 constexpr int kClusterSmemSlots = 4096;  // K2: hash slots (cells) in shared memory; 16-bit tables -> 66 KB per CTA, 3 CTAs per SM
 constexpr int kClusterMaxOcc = 3072;     // K2: more occupied cells than this -> the frame goes to the global-memory tables
 constexpr int kClusterBitmapRows = 2944; // K2: occupancy bitmap rows (ncy*ncz) that fit the shared-memory layout
-constexpr int kClusterQueue = 160;       // K2: per-warp queue of (cell, neighbour) pairs: 32 lanes x 5 dx
+constexpr int kClusterQueue = 192;       // K2: per-warp queue of (cell, neighbour) pairs: 32 lanes x 5 dx of a round + up to 31 waiting
 constexpr int kPlaneThreads = 128;    // K3/K4 CTA size == canonical reduction width of their double sums
 // K5: one CTA per (frame, colour hypothesis); the CTA is a team of T warps that share the solve.  T is chosen per
 // launch so that the batch fills the machine (launch_board_fit): 2 for large batches, 4 / 8 for small ones, where the

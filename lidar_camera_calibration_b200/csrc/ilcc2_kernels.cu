@@ -360,17 +360,22 @@ __device__ __forceinline__ unsigned hash_cell(int k) {
 // cell key: x | y << 10 | z << 20 (each axis < 1024 cells; checked at handle creation)
 __device__ __forceinline__ int pack_cell(int x, int y, int z) { return x | (y << 10) | (z << 20); }
 
-template <typename NxtT>
-__device__ __forceinline__ void join_cells(const float4* __restrict__ P, const int* key, const NxtT* head,
-                                           const NxtT* nxt, NxtT* parent, int mask, int a, int kb, float tol2) {
+// Slot of cell `kb` in the open-addressing table, or -1 when the cell is not occupied.
+__device__ __forceinline__ int find_cell(const int* key, int mask, int kb) {
   unsigned h = hash_cell(kb) & mask;
   for (;;) {
     const int kk = key[h];
-    if (kk == kb) break;
-    if (kk == -1) return;  // not occupied
+    if (kk == kb) return (int)h;
+    if (kk == -1) return -1;
     h = (h + 1) & mask;
   }
-  const int ha = (int)head[a], hb = (int)head[(int)h];
+}
+
+// Link the cells whose point lists start at ha / hb as soon as one point pair is closer than tol (nothing to do when
+// they already share a root).
+template <typename NxtT>
+__device__ __forceinline__ void pair_join(const float4* __restrict__ P, const NxtT* nxt, NxtT* parent, int ha, int hb,
+                                          float tol2) {
   if (uf_find(parent, ha) == uf_find(parent, hb)) return;
   constexpr int kEnd = (NxtT)(-1);
   for (int pa = ha; pa != kEnd; pa = (int)nxt[pa]) {
@@ -399,6 +404,7 @@ __global__ void __launch_bounds__(kClusterThreads, SMEM ? 3 : 1) cluster_kernel(
   __shared__ int s_nocc, s_nkept, s_chosen_root, s_slot;
   __shared__ unsigned s_queue_fallback[SMEM ? 1 : (NT / 32) * kClusterQueue];  // code words
   __shared__ int s_queue_slot[SMEM ? 1 : (NT / 32) * kClusterQueue];         // slot ids (do not fit 13 bits)
+  __shared__ int s_q2[2][(NT / 32) * 64];  // per-warp second queue: list heads of the cell pairs whose roots differ
 
   const int f = blockIdx.x + w.frame_base, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   ilcc2_diag* d = w.diag + f;
@@ -502,6 +508,40 @@ __global__ void __launch_bounds__(kClusterThreads, SMEM ? 3 : 1) cluster_kernel(
   // 2. join neighbouring cells: G lanes per cell, lane r of a group owns row r of the forward (dy,dz) rows
   const int nocc = s_nocc;
   const float tol2 = p.tol2;
+  int* q2a = s_q2[0] + warp * 64;
+  int* q2b = s_q2[1] + warp * 64;
+  int n2 = 0, qn = 0;  // pairs waiting in the second / first queue of this warp
+  // stage 1 for queue entry e of every lane (`act`: the lane has one), then stage 2 whenever 32 pairs have come together
+  auto drain = [&](int e, bool act) {
+    int ha = 0, hb = 0;
+    bool need = false;
+    if (act) {
+      const unsigned q = queue[e];
+      const int qa = SMEM ? (int)(q & 8191u) : qslot[e];
+      const int bit = (int)((q >> 13) & 7u), r = (int)(q >> 16);
+      const int ka = key[qa];
+      const int bx = (ka & 1023) + bit - 2, by = ((ka >> 10) & 1023) + c_row_dy[r], bz = (ka >> 20) + c_row_dz[r];
+      const int hs = find_cell(key, mask, pack_cell(bx, by, bz));
+      if (hs >= 0) {
+        ha = (int)head[qa];
+        hb = (int)head[hs];
+        need = uf_find(parent, ha) != uf_find(parent, hb);
+      }
+    }
+    const unsigned m = __ballot_sync(FULL, need);
+    if (need) {
+      const int at = n2 + __popc(m & ((1u << lane) - 1u));
+      q2a[at] = ha;
+      q2b[at] = hb;
+    }
+    n2 += __popc(m);
+    __syncwarp();
+    if (n2 >= 32) {
+      n2 -= 32;
+      pair_join<NxtT>(P, nxt, parent, q2a[n2 + lane], q2b[n2 + lane], tol2);
+      __syncwarp();
+    }
+  };
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
     // pass 0: the 13 offsets of the 3x3x3 core (5 rows x dx in [-1,1]); pass 1: the 49 outer ones (13 rows)
@@ -551,7 +591,7 @@ __global__ void __launch_bounds__(kClusterThreads, SMEM ? 3 : 1) cluster_kernel(
         if (lane >= o) incl += t;
       }
       const int total = __shfl_sync(FULL, incl, 31);
-      int off = incl - cnt;
+      int off = qn + incl - cnt;  // behind the pairs earlier rounds left in the queue (fewer than 32)
       const int rcode = pass == 0 ? (gl == 0 ? 0 : gl == 1 ? 1 : gl + 2) : gl;
       while (want) {
         const int bit = __ffs(want) - 1;
@@ -564,16 +604,21 @@ __global__ void __launch_bounds__(kClusterThreads, SMEM ? 3 : 1) cluster_kernel(
         }
       }
       __syncwarp();
-      for (int e = lane; e < total; e += 32) {
-        const unsigned q = queue[e];
-        const int qa = SMEM ? (int)(q & 8191u) : qslot[e];
-        const int bit = (int)((q >> 13) & 7u), r = (int)(q >> 16);
-        const int ka = key[qa];
-        const int bx = (ka & 1023) + bit - 2, by = ((ka >> 10) & 1023) + c_row_dy[r], bz = (ka >> 20) + c_row_dz[r];
-        join_cells<NxtT>(P, key, head, nxt, parent, mask, qa, pack_cell(bx, by, bz), tol2);
+      // (c) two stages, so that the lanes of a warp do the same kind of work at the same time (a single stage ran
+      // with 8 of 32 lanes active: most pairs end at the root comparison, a few walk two point lists).  Stage 1, one
+      // pair per lane: find the neighbour's slot, compare the roots of the two cells.  Pairs whose roots differ are
+      // compacted into a second per-warp queue; stage 2 takes 32 of them at a time (distance tests + union).
+      // The queue is drained 32 pairs at a time (a round adds ~12 pairs per warp); what is left stays for the next round.
+      qn += total;
+      while (qn >= 32) {
+        qn -= 32;
+        drain(qn + lane, true);
       }
-      __syncwarp();
     }
+    if (qn > 0) drain(lane, lane < qn);  // the pairs left over from this pass
+    qn = 0;
+    if (lane < n2) pair_join<NxtT>(P, nxt, parent, q2a[lane], q2b[lane], tol2);  // the pairs left over from this pass
+    n2 = 0;
     __syncthreads();
   }
   // 3. roots, sizes, lowest index per component (key/head tables are free now)
