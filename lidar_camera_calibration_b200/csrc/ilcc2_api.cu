@@ -229,6 +229,7 @@ void derive(const ilcc2_params& p, DevParams& d) {
   d.roi_hz = p.roi_half_z;
   d.tol2 = (float)((double)p.cluster_tolerance * (double)p.cluster_tolerance);
   d.cell = (float)(0.95 * (double)p.cluster_tolerance / std::sqrt(3.0));
+  d.inv_cell = (float)(1.0 / (double)d.cell);
   d.ncx = (int)std::floor(2.0 * p.roi_half_x / d.cell) + 2;
   d.ncy = (int)std::floor(2.0 * p.roi_half_y / d.cell) + 2;
   d.ncz = (int)std::floor(2.0 * p.roi_half_z / d.cell) + 2;

@@ -13,6 +13,7 @@ struct DevParams {
   float roi_hx, roi_hy, roi_hz;
   float tol2;            // (float)(tol*tol): FLANN radius search compares squared distances
   float cell;            // cluster hash cell edge = 0.95 * tol / sqrt(3): same cell => linked
+  float inv_cell;        // 1 / cell (the 5 % slack of the cell edge covers the rounding of x * inv_cell vs x / cell)
   int ncx, ncy, ncz;     // cells per axis over the ROI box
   int min_cl, max_cl;
   double ransac_thr;

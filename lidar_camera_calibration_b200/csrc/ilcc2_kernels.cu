@@ -477,9 +477,9 @@ __global__ void __launch_bounds__(kClusterThreads, SMEM ? 3 : 1) cluster_kernel(
   // 1. insert points into the cell hash; per-cell linked lists; occupancy bitmap
   for (int i = tid; i < M; i += NT) {
     const float4 q = P[i];
-    int cx = (int)floorf((q.x - lim[0]) / p.cell);
-    int cy = (int)floorf((q.y - lim[2]) / p.cell);
-    int cz = (int)floorf((q.z - lim[4]) / p.cell);
+    int cx = (int)floorf((q.x - lim[0]) * p.inv_cell);
+    int cy = (int)floorf((q.y - lim[2]) * p.inv_cell);
+    int cz = (int)floorf((q.z - lim[4]) * p.inv_cell);
     cx = min(max(cx, 0), p.ncx - 1);
     cy = min(max(cy, 0), p.ncy - 1);
     cz = min(max(cz, 0), p.ncz - 1);
@@ -583,25 +583,23 @@ __global__ void __launch_bounds__(kClusterThreads, SMEM ? 3 : 1) cluster_kernel(
         }
       }
       // (b) compact the (cell, neighbour) pairs of the warp into its queue: all lanes then work on real pairs
-      const int cnt = __popc(want);
-      int incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += t;
-      }
-      const int total = __shfl_sync(FULL, incl, 31);
-      int off = qn + incl - cnt;  // behind the pairs earlier rounds left in the queue (fewer than 32)
+      // one ballot per dx: the lanes that want this neighbour append behind each other (uniform, no scan, no per-lane loop)
       const int rcode = pass == 0 ? (gl == 0 ? 0 : gl == 1 ? 1 : gl + 2) : gl;
-      while (want) {
-        const int bit = __ffs(want) - 1;
-        want &= want - 1;
-        if (SMEM) {
-          queue[off++] = (unsigned)a | ((unsigned)bit << 13) | ((unsigned)rcode << 16);
-        } else {
-          qslot[off] = a;
-          queue[off++] = ((unsigned)bit << 13) | ((unsigned)rcode << 16);
+      const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+      for (int bit = 0; bit < 5; ++bit) {
+        const bool on = (want >> bit) & 1u;
+        const unsigned mb = __ballot_sync(FULL, on);
+        if (on) {
+          const int at = qn + __popc(mb & lt);
+          if (SMEM) {
+            queue[at] = (unsigned)a | ((unsigned)bit << 13) | ((unsigned)rcode << 16);
+          } else {
+            qslot[at] = a;
+            queue[at] = ((unsigned)bit << 13) | ((unsigned)rcode << 16);
+          }
         }
+        qn += __popc(mb);
       }
       __syncwarp();
       // (c) two stages, so that the lanes of a warp do the same kind of work at the same time (a single stage ran
@@ -609,7 +607,6 @@ __global__ void __launch_bounds__(kClusterThreads, SMEM ? 3 : 1) cluster_kernel(
       // pair per lane: find the neighbour's slot, compare the roots of the two cells.  Pairs whose roots differ are
       // compacted into a second per-warp queue; stage 2 takes 32 of them at a time (distance tests + union).
       // The queue is drained 32 pairs at a time (a round adds ~12 pairs per warp); what is left stays for the next round.
-      qn += total;
       while (qn >= 32) {
         qn -= 32;
         drain(qn + lane, true);
