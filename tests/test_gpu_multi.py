@@ -49,3 +49,19 @@ def test_cpp_host_gathers_every_ranks_corners(product_lib, tmp_path, world):
             got_s = raw[N * 35 * 12:].view(np.int32)
             assert np.array_equal(got_s, want_s), (step, rank)
             assert np.array_equal(got_c, want_c, equal_nan=True), (step, rank)
+
+
+@pytest.mark.skipif(_gpus() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("parts,multicast", [(2, 1), (3, 1), (3, 0)])
+def test_fused_gather_lanes(product_lib, parts, multicast):
+    """dist.FusedGather under pipelined lanes on two GPUs (torchrun): inline barrier (2 parts) and the barrier on a side
+    stream one step behind the lane (3 parts), through the NVLS multicast mapping and with peer stores; seven steps on
+    different frames, every step's gathered corners equal to a plain NCCL all-gather on every rank."""
+    import sys
+    worker = os.path.join(ROOT, "tests", "helpers", "fused_gather_worker.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29530 + parts * 2 + multicast),
+                        worker, str(parts), str(multicast)], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-600:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "ok True" in r.stdout
