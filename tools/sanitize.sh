@@ -1,6 +1,6 @@
 #!/bin/bash
 # compute-sanitizer over one pass of the hot path (device path) and one host-path call (staging rings), small batches
-OUT=gpurun_out/sanitizer_r2.txt
+OUT=${SAN_OUT:-gpurun_out/sanitizer_r2.txt}
 : > $OUT
 for F in 40 400; do
   echo "== memcheck, $F frames (device path)" >> $OUT
