@@ -219,7 +219,8 @@ class PipelinedExtractor:
     so the kernels of batch k+1 (K1-K4, then the first wave of K5) run on the SMs that the tail of batch k's K5 leaves
     idle -- K5 is a chain of ~100 dependent evaluations per solve, its last CTAs keep a few SMs busy for the length of
     a whole solve.  Every batch goes through exactly the same launches as with one handle (results are identical); only
-    their placement in time changes.  Two lanes are enough (measured: 2.11 -> 1.83 ms per 1024 frames; 3 / 4 lanes 1.87 / 1.92).
+    their placement in time changes.  Measured per 1024 frames: one handle 2.02 ms, three lanes 1.63 ms (K5 then runs one
+    warp per solve: ilcc2_set_lanes), four lanes 1.62.
 
     submit() makes the lane's stream wait for the caller's current stream (inputs are ready), enqueues the batch, and
     returns the lane; join() makes a stream wait for everything submitted so far.  Output buffers of a lane must not be
